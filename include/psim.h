@@ -1,0 +1,158 @@
+/*
+ * psim.h -- C ABI of libpsim: the B200 (sm_100a) implementation of the reference's per-timestep
+ * hot path (cell binning -> 3x3-neighbourhood short-range force -> move with reflective walls).
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes (no C++ or torch types) and
+ * returns an int status (PSIM_OK == 0).  The reference has no error channel (void functions; its
+ * CUDA part prints "GPUassert: ..." and exits, reference part3/gpu.cu:70-77); the C++ shim
+ * (csrc/psim_shim.cpp) that exports the reference's two mangled C++ names maps a non-zero status
+ * to exactly that behaviour.
+ *
+ * There is NO CPU fallback: every function that computes needs a CUDA device and fails with
+ * PSIM_ERR_NO_DEVICE / PSIM_ERR_CUDA otherwise.
+ *
+ * Reference interface replaced by each group (paths relative to the reference repository):
+ *   psim_create            init_simulation      part1/serial.cpp:76-88, part1/openmp.cpp:42-66,
+ *                                               part3/gpu.cu:174-185   (+ the H2D upload of
+ *                                               part3/main.cu:120-122 when `parts` is a host pointer)
+ *   psim_step              simulate_one_step    part1/serial.cpp:119-131, part1/openmp.cpp:69-83,
+ *                                               part3/gpu.cu:187-208   (n calls fused into one batch)
+ *   psim_read_particles    the driver's view of `parts` after a step: part1/main.cpp:135-136 (host),
+ *                                               part3/main.cu:134-136 (device array + cudaMemcpy D2H)
+ *   psim_read_cells        the bin structure    part1/serial.cpp:14-16,41-43,84-86;
+ *                                               part3/gpu.cu:92-112 (Bins / Bin_Sizes)
+ *   psim_stats             (no reference code; validation statistics of SURVEY.md section 8c-5)
+ *   psim_init_particles    init_particles       part1/main.cpp:31-59
+ *   psim_save_frame        save                 part1/main.cpp:15-28
+ */
+#ifndef PSIM_H
+#define PSIM_H
+
+#include "psim_common.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---- */
+#define PSIM_OK               0
+#define PSIM_ERR_INVALID      1  /* bad argument / bad handle                                   */
+#define PSIM_ERR_NO_DEVICE    2  /* no usable CUDA device (there is no CPU path)                */
+#define PSIM_ERR_CUDA         3  /* a CUDA runtime call or kernel failed                        */
+#define PSIM_ERR_CAPACITY     4  /* a tile / halo list / migration outbox overflowed on device  */
+#define PSIM_ERR_STATE        5  /* call not valid in the current state                         */
+#define PSIM_ERR_COMM         6  /* NCCL / multi-GPU exchange failure                           */
+#define PSIM_ERR_UNSUPPORTED  7  /* configuration the selected engine cannot run                */
+
+/* ---- engines ---- */
+#define PSIM_ENGINE_AUTO      0  /* tiled when the particle density fits its tiles, else cellsort */
+#define PSIM_ENGINE_CELLSORT  1  /* per step: atomic histogram over cutoff cells, single-pass
+                                    exclusive scan, scatter into cell-sorted SoA, force+move     */
+#define PSIM_ENGINE_TILED     2  /* persistent tile-resident SoA; one fused kernel per step does
+                                    in-shared-memory binning, force, move, re-tiling, halo export */
+
+/* flags for psim_step */
+#define PSIM_STEP_DEFAULT     0  /* accelerations are materialised for the LAST step of the batch */
+#define PSIM_STEP_ACCEL_ALL   1  /* store ax, ay after every step of the batch                    */
+#define PSIM_STEP_ACCEL_NONE  2  /* never store ax, ay (read-back then returns the last stored)   */
+
+typedef struct psim_sim psim_sim; /* opaque */
+
+typedef struct psim_config {
+    int   engine;        /* PSIM_ENGINE_*                                                        */
+    int   device;        /* CUDA device ordinal; -1 = the calling thread's current device        */
+    void* stream;        /* cudaStream_t to run on; NULL = a private non-blocking stream         */
+    int   tile_cells;    /* tiled engine: cutoff cells per tile side (16, 32 or 64); 0 = auto    */
+    int   use_graph;     /* tiled engine: replay steps through a CUDA graph (0/1); -1 = auto     */
+    /* 1-D slab decomposition.  nranks == 1: the whole box.               */
+    int   rank;          /* this slab's index along x (cell rows)                                */
+    int   nranks;        /* number of slabs                                                      */
+    int   reserved[8];
+} psim_config;
+
+typedef struct psim_stats_t {
+    double dmin;           /* min r/cutoff over ordered in-range pairs (1.0 if none)            */
+    double davg;           /* mean r/cutoff over ordered in-range pairs                         */
+    double kinetic_energy; /* sum 0.5 m v^2                                                     */
+    double vmax;           /* max |v|                                                           */
+    long long pairs;       /* ordered in-range pairs (i, j != i)                                */
+    long long touched;     /* particles with >= 1 in-range neighbour                            */
+    int    max_neighbours; /* max in-range neighbours of one particle                           */
+    int    max_cell_count; /* max population of one cutoff cell                                 */
+} psim_stats_t;
+
+typedef struct psim_info_t {
+    int engine;            /* engine actually selected                                          */
+    int bin_count;         /* cutoff cells per box side = ceil(size / 0.01)                     */
+    int tile_cells;        /* tiled engine: cells per tile side                                 */
+    int tiles_per_side;
+    int tile_capacity;     /* particle slots per tile                                           */
+    int device;
+    int num_parts;         /* particles owned by this slab right now                            */
+    int rank, nranks;
+    int row_begin, row_end;/* cell rows [begin, end) owned by this slab                         */
+    long long steps_done;
+    long long kernel_launches; /* kernels this handle launched so far                           */
+    long long device_bytes;    /* device memory held                                            */
+} psim_info_t;
+
+/* ---- errors ---- */
+const char* psim_error_string(int status);
+/* detail of the last failure on the calling thread ("" if none) */
+const char* psim_last_error(void);
+
+/* ---- lifecycle ---- */
+void psim_config_default(psim_config* cfg);
+/* cells per side, ceil(size / 0.01): reference part1/serial.cpp:78 */
+int  psim_bin_count(double size);
+
+/* Build the simulation state from `num_parts` AoS records.  `parts` may be a host pointer
+ * (part1/main.cpp flavour) or a device pointer (part3/main.cu flavour); the kind is detected.
+ * ax, ay of the input are ignored (the reference driver leaves them uninitialised).
+ * With nranks > 1 the slab keeps only the particles whose cell row falls in its row range. */
+int psim_create(psim_sim** out, const psim_config* cfg, const particle_t* parts, int num_parts, double size);
+int psim_destroy(psim_sim* sim);
+
+/* ---- stepping ---- */
+/* Enqueue `nsteps` time steps on the handle's stream (asynchronous). */
+int psim_step(psim_sim* sim, int nsteps, int flags);
+/* Wait for the stream and report sticky device-side errors (capacity overflow etc.). */
+int psim_sync(psim_sim* sim);
+
+/* ---- observation (all of these synchronise) ---- */
+/* Write the current state, in ORIGINAL particle order, to `dst` (host or device pointer, the
+ * caller's full array of `num_parts_total` records; a slab only writes the particles it owns).
+ * Fields: x y vx vy of the current step; ax ay = the acceleration used by the last step whose
+ * accelerations were stored (see PSIM_STEP_*). */
+int psim_read_particles(psim_sim* sim, particle_t* dst);
+/* positions only: xy[2*i] = x_i, xy[2*i+1] = y_i, host or device pointer */
+int psim_read_positions(psim_sim* sim, double* xy);
+/* cell_of_particle[i] = row*bin_count+col with row = floor(x/0.01), col = floor(y/0.01)
+ * (bit-exact IEEE division, reference part1/serial.cpp:41-43); cell_counts[c] = population of
+ * cell c (bin_count^2 ints).  Either pointer may be NULL.  HOST pointers. */
+int psim_read_cells(psim_sim* sim, int* cell_of_particle, int* cell_counts);
+/* membership lists in CSR form (the reference's Bins): cell_start has bin_count^2+1 entries,
+ * members has num_parts entries, members of a cell in ascending original index.  HOST pointers. */
+int psim_read_cell_lists(psim_sim* sim, int* cell_start, int* members);
+int psim_stats(psim_sim* sim, psim_stats_t* out);
+int psim_info(psim_sim* sim, psim_info_t* out);
+
+/* ---- driver helpers (host side) ---- */
+/* The reference driver's particle generator: std::mt19937(seed), shuffled lattice, float
+ * velocities in [-1,1) -- reference part1/main.cpp:31-59.  seed 0 = std::random_device.
+ * ax, ay are set to 0. */
+int psim_init_particles(particle_t* parts_host, int num_parts, double size, int seed);
+/* Append one frame to an open trajectory file in the reference's text format
+ * (part1/main.cpp:15-28): first call writes "N size", every call N lines "x y" + blank line.
+ * `file` is a FILE*; `xy` the interleaved positions from psim_read_positions. */
+int psim_save_frame(void* file, const double* xy, int num_parts, double size, int first);
+
+/* ---- multi-GPU slab exchange (one process per GPU) ---- */
+/* 128-byte NCCL unique id: rank 0 creates it, the launcher broadcasts it, every rank connects. */
+int psim_comm_unique_id(unsigned char id128[128]);
+int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSIM_H */

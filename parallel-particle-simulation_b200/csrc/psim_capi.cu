@@ -1,0 +1,585 @@
+// psim_capi.cu -- the extern "C" boundary (include/psim.h): handle life cycle, engine dispatch,
+// observation kernels (original-order read-back, cell ids / counts / lists, statistics).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "psim_device.cuh"
+#include "psim_internal.h"
+
+namespace psim {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int fail(int status, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------
+// observation kernels
+// ------------------------------------------------------------------------------------------
+constexpr int kObsThreads = 256;
+
+// compact SoA -> caller's AoS in original order (reference part1/common.h:14-21 record)
+__global__ void __launch_bounds__(kObsThreads) soa_to_aos_kernel(SoAView v, bool have_acc, particle_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    double2* q = reinterpret_cast<double2*>(out + v.id[i]);
+    q[0] = make_double2(v.x[i], v.y[i]);
+    q[1] = make_double2(v.vx[i], v.vy[i]);
+    q[2] = have_acc ? make_double2(v.ax[i], v.ay[i]) : make_double2(0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(kObsThreads) soa_to_xy_kernel(SoAView v, double2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    out[v.id[i]] = make_double2(v.x[i], v.y[i]);
+}
+
+// compact records for the multi-slab host path: rec[i] = {x y vx vy ax ay}
+__global__ void __launch_bounds__(kObsThreads) soa_pack_kernel(SoAView v, bool have_acc, particle_t* __restrict__ rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    double2* q = reinterpret_cast<double2*>(rec + i);
+    q[0] = make_double2(v.x[i], v.y[i]);
+    q[1] = make_double2(v.vx[i], v.vy[i]);
+    q[2] = have_acc ? make_double2(v.ax[i], v.ay[i]) : make_double2(0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(kObsThreads) cell_of_particle_kernel(SoAView v, int bincnt, int* __restrict__ cell_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    cell_of[v.id[i]] = axis_cell(v.x[i], bincnt) * bincnt + axis_cell(v.y[i], bincnt);
+}
+
+// members in arrival order, then ranked by original index inside each cell
+__global__ void __launch_bounds__(kObsThreads) members_raw_kernel(SoAView v, int bincnt, const int* __restrict__ cell_start,
+                                                                  const int* __restrict__ slot, int* __restrict__ raw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const int c = axis_cell(v.x[i], bincnt) * bincnt + axis_cell(v.y[i], bincnt);
+    raw[cell_start[c] + slot[i]] = v.id[i];
+}
+__global__ void __launch_bounds__(kObsThreads) members_rank_kernel(SoAView v, int bincnt, const int* __restrict__ cell_start,
+                                                                   const int* __restrict__ raw, int* __restrict__ members) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const int c = axis_cell(v.x[i], bincnt) * bincnt + axis_cell(v.y[i], bincnt);
+    const int s = cell_start[c], e = cell_start[c + 1], me = v.id[i];
+    int rank = 0;
+    for (int k = s; k < e; ++k) rank += raw[k] < me;
+    members[s + rank] = me;
+}
+
+// sorted copies of the positions for the statistics pass
+__global__ void __launch_bounds__(kObsThreads) sort_xy_kernel(SoAView v, int bincnt, const int* __restrict__ cell_start,
+                                                              const int* __restrict__ slot, double* __restrict__ sx,
+                                                              double* __restrict__ sy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const int c = axis_cell(v.x[i], bincnt) * bincnt + axis_cell(v.y[i], bincnt);
+    const int d = cell_start[c] + slot[i];
+    sx[d] = v.x[i];
+    sy[d] = v.y[i];
+}
+
+struct StatsPartial {
+    double dmin, dsum, ke, vmax;
+    long long pairs, touched;
+    int maxnb, maxcell;
+};
+
+__global__ void __launch_bounds__(kObsThreads) stats_kernel(const double* __restrict__ sx, const double* __restrict__ sy, int n,
+                                                            SoAView v, int bincnt, const int* __restrict__ cell_start,
+                                                            StatsPartial* __restrict__ partial) {
+    __shared__ StatsPartial s_part[kObsThreads / 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    StatsPartial p{1.0, 0.0, 0.0, 0.0, 0, 0, 0, 0};
+    if (i < n) {
+        const double xi = sx[i], yi = sy[i];
+        const int row = axis_cell(xi, bincnt), col = axis_cell(yi, bincnt);
+        const int c_lo = max(col - 1, 0), c_hi = min(col + 1, bincnt - 1);
+        int nb = 0;
+        for (int dr = -1; dr <= 1; ++dr) {
+            const int rr = row + dr;
+            if (rr < 0 || rr >= bincnt) continue;
+            const long long b = (long long)rr * bincnt;
+            for (int k = cell_start[b + c_lo]; k < cell_start[b + c_hi + 1]; ++k) {
+                if (k == i) continue;
+                const double dx = __dsub_rn(sx[k], xi), dy = __dsub_rn(sy[k], yi);
+                const double r2 = pair_r2(dx, dy);
+                if (r2 > kCutoff2) continue;
+                const double d = __ddiv_rn(__dsqrt_rn(r2), kCutoff);
+                p.dmin = fmin(p.dmin, d);
+                p.dsum += d;
+                ++nb;
+            }
+        }
+        p.pairs = nb;
+        p.touched = nb > 0;
+        p.maxnb = nb;
+        const long long c = (long long)row * bincnt + col;
+        p.maxcell = cell_start[c + 1] - cell_start[c];
+        const double vx = v.vx[i], vy = v.vy[i];  // any order: kinetic terms are per particle
+        const double v2 = vx * vx + vy * vy;
+        p.ke = 0.5 * kMass * v2;
+        p.vmax = sqrt(v2);
+    }
+    // warp, then block reduction
+    for (int o = 16; o > 0; o >>= 1) {
+        p.dmin = fmin(p.dmin, __shfl_xor_sync(0xffffffffu, p.dmin, o));
+        p.dsum += __shfl_xor_sync(0xffffffffu, p.dsum, o);
+        p.ke += __shfl_xor_sync(0xffffffffu, p.ke, o);
+        p.vmax = fmax(p.vmax, __shfl_xor_sync(0xffffffffu, p.vmax, o));
+        p.pairs += __shfl_xor_sync(0xffffffffu, p.pairs, o);
+        p.touched += __shfl_xor_sync(0xffffffffu, p.touched, o);
+        p.maxnb = max(p.maxnb, __shfl_xor_sync(0xffffffffu, p.maxnb, o));
+        p.maxcell = max(p.maxcell, __shfl_xor_sync(0xffffffffu, p.maxcell, o));
+    }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StatsPartial t = s_part[0];
+        for (int w = 1; w < kObsThreads / 32; ++w) {
+            const StatsPartial& q = s_part[w];
+            t.dmin = fmin(t.dmin, q.dmin);
+            t.dsum += q.dsum;
+            t.ke += q.ke;
+            t.vmax = fmax(t.vmax, q.vmax);
+            t.pairs += q.pairs;
+            t.touched += q.touched;
+            t.maxnb = max(t.maxnb, q.maxnb);
+            t.maxcell = max(t.maxcell, q.maxcell);
+        }
+        partial[blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+static bool pointer_on_device(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int view_of(psim_sim* sim, SoAView* v, bool* have_acc) {
+    if (sim->engine == PSIM_ENGINE_CELLSORT) {
+        PSIM_TRY(cellsort_view(sim, v));
+        *have_acc = true;
+    } else {
+        PSIM_TRY(tiled_view(sim, v));
+        *have_acc = true;  // the gather already substitutes zeros when accelerations are stale
+    }
+    return PSIM_OK;
+}
+
+static int check_device_error(psim_sim* sim) {
+    PSIM_CUDA(cudaMemcpyAsync(sim->h_err, sim->d_err, sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+    PSIM_CUDA(cudaStreamSynchronize(sim->stream));
+    const int e = *sim->h_err;
+    if (e == 0) return PSIM_OK;
+    return fail(PSIM_ERR_CAPACITY, "device capacity error 0x%x:%s%s%s%s%s", e, (e & kErrTileOverflow) ? " tile-overflow" : "",
+                (e & kErrHaloOverflow) ? " halo-list-overflow" : "", (e & kErrOutboxOverflow) ? " outbox-overflow" : "",
+                (e & kErrSmemOverflow) ? " apron-staging-overflow" : "", (e & kErrLostParticle) ? " particle-skipped-a-tile" : "");
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace psim
+
+using namespace psim;
+
+extern "C" {
+
+const char* psim_error_string(int status) {
+    switch (status) {
+        case PSIM_OK: return "ok";
+        case PSIM_ERR_INVALID: return "invalid argument";
+        case PSIM_ERR_NO_DEVICE: return "no CUDA device (libpsim has no CPU path)";
+        case PSIM_ERR_CUDA: return "CUDA error";
+        case PSIM_ERR_CAPACITY: return "device-side capacity overflow";
+        case PSIM_ERR_STATE: return "invalid state";
+        case PSIM_ERR_COMM: return "communication error";
+        case PSIM_ERR_UNSUPPORTED: return "unsupported configuration";
+    }
+    return "unknown status";
+}
+
+const char* psim_last_error(void) { return g_last_error.c_str(); }
+
+void psim_config_default(psim_config* cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->engine = PSIM_ENGINE_AUTO;
+    cfg->device = -1;
+    cfg->use_graph = -1;
+    cfg->nranks = 1;
+}
+
+int psim_bin_count(double size) { return (int)std::ceil(size / PSIM_BIN_SIZE); }
+
+int psim_create(psim_sim** out, const psim_config* cfg_in, const particle_t* parts, int num_parts, double size) {
+    if (!out) return fail(PSIM_ERR_INVALID, "psim_create: out is NULL");
+    *out = nullptr;
+    psim_config cfg;
+    if (cfg_in) cfg = *cfg_in;
+    else psim_config_default(&cfg);
+    if (cfg.nranks < 1) cfg.nranks = 1;
+    if (num_parts < 0 || (num_parts > 0 && !parts)) return fail(PSIM_ERR_INVALID, "psim_create: bad particle array");
+    if (!(size > 0.0) || !std::isfinite(size)) return fail(PSIM_ERR_INVALID, "psim_create: box size must be positive");
+    if (cfg.rank < 0 || cfg.rank >= cfg.nranks) return fail(PSIM_ERR_INVALID, "psim_create: rank %d of %d", cfg.rank, cfg.nranks);
+    const double nb = std::ceil(size / PSIM_BIN_SIZE);
+    if (nb < 1 || nb * nb > 2.0e9) return fail(PSIM_ERR_UNSUPPORTED, "psim_create: %g cells per side do not fit int32 cell ids", nb);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PSIM_ERR_NO_DEVICE, "psim_create: no CUDA device visible; libpsim has no CPU fallback");
+    }
+    int dev = cfg.device;
+    if (dev < 0) PSIM_CUDA(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PSIM_ERR_INVALID, "psim_create: device %d of %d", dev, ndev);
+    PSIM_CUDA(cudaSetDevice(dev));
+
+    psim_sim* sim = new psim_sim();
+    sim->device = dev;
+    sim->n_total = num_parts;
+    sim->size = size;
+    sim->bincnt = (int)nb;
+    sim->rank = cfg.rank;
+    sim->nranks = cfg.nranks;
+    sim->row_begin = 0;
+    sim->row_end = sim->bincnt;
+    auto bail = [&](int st) {
+        std::string keep = g_last_error;
+        psim_destroy(sim);
+        g_last_error = keep;
+        return st;
+    };
+    if (cfg.stream) {
+        sim->stream = static_cast<cudaStream_t>(cfg.stream);
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return bail(fail(PSIM_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
+        sim->own_stream = true;
+    }
+    int st = sim->mem.alloc(&sim->d_err, 4);
+    if (st) return bail(st);
+    if (cudaMemsetAsync(sim->d_err, 0, 4 * sizeof(int), sim->stream) != cudaSuccess ||
+        cudaHostAlloc(&sim->h_err, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+        return bail(fail(PSIM_ERR_CUDA, "psim_create: error-word allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+
+    const bool on_device = num_parts > 0 && pointer_on_device(parts);
+    int engine = cfg.engine;
+    if (engine != PSIM_ENGINE_AUTO && engine != PSIM_ENGINE_CELLSORT && engine != PSIM_ENGINE_TILED)
+        return bail(fail(PSIM_ERR_INVALID, "psim_create: unknown engine %d", engine));
+    if (engine == PSIM_ENGINE_CELLSORT && cfg.nranks > 1)
+        return bail(fail(PSIM_ERR_UNSUPPORTED, "psim_create: slabs need the tiled engine"));
+
+    if (engine == PSIM_ENGINE_AUTO || engine == PSIM_ENGINE_TILED) {
+        bool unsuitable = false;
+        st = tiled_create(sim, &cfg, parts, num_parts, on_device, &unsuitable);
+        if (st == PSIM_OK) {
+            sim->engine = PSIM_ENGINE_TILED;
+        } else if (unsuitable && engine == PSIM_ENGINE_AUTO && cfg.nranks == 1) {
+            tiled_destroy(sim);
+            engine = PSIM_ENGINE_CELLSORT;
+        } else {
+            return bail(st);
+        }
+    }
+    if (engine == PSIM_ENGINE_CELLSORT) {
+        const particle_t* d_parts = parts;
+        DeviceArena stage;
+        if (!on_device && num_parts > 0) {
+            particle_t* tmp = nullptr;
+            st = stage.alloc(&tmp, (size_t)num_parts);
+            if (st) return bail(st);
+            cudaError_t e = cudaMemcpyAsync(tmp, parts, sizeof(particle_t) * (size_t)num_parts, cudaMemcpyHostToDevice, sim->stream);
+            if (e != cudaSuccess) {
+                stage.release();
+                return bail(fail(PSIM_ERR_CUDA, "upload: %s", cudaGetErrorString(e)));
+            }
+            d_parts = tmp;
+        }
+        st = cellsort_create(sim, d_parts, num_parts);
+        cudaStreamSynchronize(sim->stream);
+        stage.release();
+        if (st) return bail(st);
+        sim->engine = PSIM_ENGINE_CELLSORT;
+    }
+    st = check_device_error(sim);
+    if (st) return bail(st);
+    *out = sim;
+    return PSIM_OK;
+}
+
+int psim_destroy(psim_sim* sim) {
+    if (!sim) return PSIM_OK;
+    cudaSetDevice(sim->device);
+    if (sim->stream) cudaStreamSynchronize(sim->stream);
+    comm_destroy(sim);
+    cellsort_destroy(sim);
+    tiled_destroy(sim);
+    sim->scratch.release();
+    sim->mem.release();
+    if (sim->h_err) cudaFreeHost(sim->h_err);
+    if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
+    delete sim;
+    return PSIM_OK;
+}
+
+int psim_step(psim_sim* sim, int nsteps, int flags) {
+    if (!sim) return fail(PSIM_ERR_INVALID, "psim_step: NULL handle");
+    if (nsteps < 0) return fail(PSIM_ERR_INVALID, "psim_step: nsteps %d", nsteps);
+    if (nsteps == 0) return PSIM_OK;
+    DeviceGuard g(sim->device);
+    return sim->engine == PSIM_ENGINE_CELLSORT ? cellsort_step(sim, nsteps, flags) : tiled_step(sim, nsteps, flags);
+}
+
+int psim_sync(psim_sim* sim) {
+    if (!sim) return fail(PSIM_ERR_INVALID, "psim_sync: NULL handle");
+    DeviceGuard g(sim->device);
+    return check_device_error(sim);
+}
+
+int psim_read_particles(psim_sim* sim, particle_t* dst) {
+    if (!sim || !dst) return fail(PSIM_ERR_INVALID, "psim_read_particles: NULL argument");
+    DeviceGuard g(sim->device);
+    PSIM_TRY(check_device_error(sim));
+    SoAView v;
+    bool acc;
+    PSIM_TRY(view_of(sim, &v, &acc));
+    cudaStream_t s = sim->stream;
+    const int blocks = (v.n + kObsThreads - 1) / kObsThreads;
+    if (pointer_on_device(dst)) {
+        if (v.n) soa_to_aos_kernel<<<blocks, kObsThreads, 0, s>>>(v, acc, dst);
+        ++sim->launches;
+        PSIM_CUDA(cudaGetLastError());
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        return PSIM_OK;
+    }
+    sim->scratch.release();
+    particle_t* stage = nullptr;
+    if (sim->nranks == 1) {
+        PSIM_TRY(sim->scratch.alloc(&stage, (size_t)sim->n_total));
+        if (v.n) soa_to_aos_kernel<<<blocks, kObsThreads, 0, s>>>(v, acc, stage);
+        ++sim->launches;
+        PSIM_CUDA(cudaGetLastError());
+        PSIM_CUDA(cudaMemcpyAsync(dst, stage, sizeof(particle_t) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
+        PSIM_CUDA(cudaStreamSynchronize(s));
+    } else {
+        // a slab writes only the records it owns: pack on the device, place on the host
+        PSIM_TRY(sim->scratch.alloc(&stage, (size_t)v.n));
+        if (v.n) soa_pack_kernel<<<blocks, kObsThreads, 0, s>>>(v, acc, stage);
+        ++sim->launches;
+        std::vector<particle_t> rec((size_t)v.n);
+        std::vector<int> ids((size_t)v.n);
+        PSIM_CUDA(cudaMemcpyAsync(rec.data(), stage, sizeof(particle_t) * (size_t)v.n, cudaMemcpyDeviceToHost, s));
+        PSIM_CUDA(cudaMemcpyAsync(ids.data(), v.id, sizeof(int) * (size_t)v.n, cudaMemcpyDeviceToHost, s));
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < v.n; ++i) dst[ids[i]] = rec[i];
+    }
+    sim->scratch.release();
+    return PSIM_OK;
+}
+
+int psim_read_positions(psim_sim* sim, double* xy) {
+    if (!sim || !xy) return fail(PSIM_ERR_INVALID, "psim_read_positions: NULL argument");
+    DeviceGuard g(sim->device);
+    PSIM_TRY(check_device_error(sim));
+    SoAView v;
+    bool acc;
+    PSIM_TRY(view_of(sim, &v, &acc));
+    cudaStream_t s = sim->stream;
+    const int blocks = (v.n + kObsThreads - 1) / kObsThreads;
+    if (pointer_on_device(xy)) {
+        if (v.n) soa_to_xy_kernel<<<blocks, kObsThreads, 0, s>>>(v, reinterpret_cast<double2*>(xy));
+        ++sim->launches;
+        PSIM_CUDA(cudaGetLastError());
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        return PSIM_OK;
+    }
+    sim->scratch.release();
+    double2* stage = nullptr;
+    PSIM_TRY(sim->scratch.alloc(&stage, (size_t)sim->n_total));
+    if (sim->nranks > 1)
+        PSIM_CUDA(cudaMemcpyAsync(stage, xy, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyHostToDevice, s));
+    if (v.n) soa_to_xy_kernel<<<blocks, kObsThreads, 0, s>>>(v, stage);
+    ++sim->launches;
+    PSIM_CUDA(cudaGetLastError());
+    PSIM_CUDA(cudaMemcpyAsync(xy, stage, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
+    PSIM_CUDA(cudaStreamSynchronize(s));
+    sim->scratch.release();
+    return PSIM_OK;
+}
+
+int psim_read_cells(psim_sim* sim, int* cell_of_particle, int* cell_counts) {
+    if (!sim) return fail(PSIM_ERR_INVALID, "psim_read_cells: NULL handle");
+    DeviceGuard g(sim->device);
+    PSIM_TRY(check_device_error(sim));
+    SoAView v;
+    bool acc;
+    PSIM_TRY(view_of(sim, &v, &acc));
+    cudaStream_t s = sim->stream;
+    const int blocks = (v.n + kObsThreads - 1) / kObsThreads;
+    if (cell_of_particle) {
+        DeviceArena tmp;
+        int* d = nullptr;
+        PSIM_TRY(tmp.alloc(&d, (size_t)sim->n_total));
+        PSIM_CUDA(cudaMemsetAsync(d, 0xFF, sizeof(int) * (size_t)sim->n_total, s));  // -1 = not owned by this slab
+        if (v.n) cell_of_particle_kernel<<<blocks, kObsThreads, 0, s>>>(v, sim->bincnt, d);
+        ++sim->launches;
+        PSIM_CUDA(cudaGetLastError());
+        PSIM_CUDA(cudaMemcpyAsync(cell_of_particle, d, sizeof(int) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        tmp.release();
+    }
+    if (cell_counts) {
+        CellBinner b;
+        int st = b.init(sim->bincnt, std::max(v.n, 1));
+        if (st == PSIM_OK) st = b.count(v.x, v.y, v.n, s);
+        if (st == PSIM_OK) {
+            cudaError_t e = cudaMemcpyAsync(cell_counts, b.cell_start, sizeof(int) * (size_t)b.ncell, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) st = fail(PSIM_ERR_CUDA, "psim_read_cells: %s", cudaGetErrorString(e));
+        }
+        sim->launches += b.launches;
+        b.release();
+        PSIM_TRY(st);
+    }
+    return PSIM_OK;
+}
+
+int psim_read_cell_lists(psim_sim* sim, int* cell_start, int* members) {
+    if (!sim || !cell_start || !members) return fail(PSIM_ERR_INVALID, "psim_read_cell_lists: NULL argument");
+    DeviceGuard g(sim->device);
+    PSIM_TRY(check_device_error(sim));
+    SoAView v;
+    bool acc;
+    PSIM_TRY(view_of(sim, &v, &acc));
+    cudaStream_t s = sim->stream;
+    const int blocks = (v.n + kObsThreads - 1) / kObsThreads;
+    CellBinner b;
+    DeviceArena tmp;
+    int *raw = nullptr, *mem = nullptr;
+    int st = b.init(sim->bincnt, std::max(v.n, 1));
+    if (st == PSIM_OK) st = b.build(v.x, v.y, v.n, s);
+    if (st == PSIM_OK) st = tmp.alloc(&raw, (size_t)v.n);
+    if (st == PSIM_OK) st = tmp.alloc(&mem, (size_t)v.n);
+    if (st == PSIM_OK && v.n) {
+        members_raw_kernel<<<blocks, kObsThreads, 0, s>>>(v, sim->bincnt, b.cell_start, b.slot, raw);
+        members_rank_kernel<<<blocks, kObsThreads, 0, s>>>(v, sim->bincnt, b.cell_start, raw, mem);
+        sim->launches += 2;
+    }
+    if (st == PSIM_OK) {
+        cudaError_t e = cudaMemcpyAsync(cell_start, b.cell_start, sizeof(int) * ((size_t)b.ncell + 1), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && v.n) e = cudaMemcpyAsync(members, mem, sizeof(int) * (size_t)v.n, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) st = fail(PSIM_ERR_CUDA, "psim_read_cell_lists: %s", cudaGetErrorString(e));
+    }
+    sim->launches += b.launches;
+    b.release();
+    tmp.release();
+    return st;
+}
+
+int psim_stats(psim_sim* sim, psim_stats_t* out) {
+    if (!sim || !out) return fail(PSIM_ERR_INVALID, "psim_stats: NULL argument");
+    DeviceGuard g(sim->device);
+    PSIM_TRY(check_device_error(sim));
+    SoAView v;
+    bool acc;
+    PSIM_TRY(view_of(sim, &v, &acc));
+    cudaStream_t s = sim->stream;
+    std::memset(out, 0, sizeof *out);
+    out->dmin = 1.0;
+    if (v.n == 0) return PSIM_OK;
+    const int blocks = (v.n + kObsThreads - 1) / kObsThreads;
+    CellBinner b;
+    DeviceArena tmp;
+    double *sx = nullptr, *sy = nullptr;
+    StatsPartial* part = nullptr;
+    int st = b.init(sim->bincnt, v.n);
+    if (st == PSIM_OK) st = b.build(v.x, v.y, v.n, s);
+    if (st == PSIM_OK) st = tmp.alloc(&sx, (size_t)v.n);
+    if (st == PSIM_OK) st = tmp.alloc(&sy, (size_t)v.n);
+    if (st == PSIM_OK) st = tmp.alloc(&part, (size_t)blocks);
+    std::vector<StatsPartial> h((size_t)blocks);
+    if (st == PSIM_OK) {
+        sort_xy_kernel<<<blocks, kObsThreads, 0, s>>>(v, sim->bincnt, b.cell_start, b.slot, sx, sy);
+        stats_kernel<<<blocks, kObsThreads, 0, s>>>(sx, sy, v.n, v, sim->bincnt, b.cell_start, part);
+        sim->launches += 2;
+        cudaError_t e = cudaMemcpyAsync(h.data(), part, sizeof(StatsPartial) * (size_t)blocks, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) st = fail(PSIM_ERR_CUDA, "psim_stats: %s", cudaGetErrorString(e));
+    }
+    sim->launches += b.launches;
+    b.release();
+    tmp.release();
+    PSIM_TRY(st);
+    double dsum = 0;
+    for (const StatsPartial& p : h) {
+        out->dmin = std::min(out->dmin, p.dmin);
+        dsum += p.dsum;
+        out->kinetic_energy += p.ke;
+        out->vmax = std::max(out->vmax, p.vmax);
+        out->pairs += p.pairs;
+        out->touched += p.touched;
+        out->max_neighbours = std::max(out->max_neighbours, p.maxnb);
+        out->max_cell_count = std::max(out->max_cell_count, p.maxcell);
+    }
+    out->davg = out->pairs ? dsum / (double)out->pairs : 0.0;
+    return PSIM_OK;
+}
+
+int psim_info(psim_sim* sim, psim_info_t* out) {
+    if (!sim || !out) return fail(PSIM_ERR_INVALID, "psim_info: NULL argument");
+    std::memset(out, 0, sizeof *out);
+    out->engine = sim->engine;
+    out->bin_count = sim->bincnt;
+    out->device = sim->device;
+    out->rank = sim->rank;
+    out->nranks = sim->nranks;
+    out->row_begin = sim->row_begin;
+    out->row_end = sim->row_end;
+    out->steps_done = sim->steps_done;
+    out->kernel_launches = sim->launches;
+    out->num_parts = sim->n_total;
+    out->device_bytes = (long long)sim->mem.bytes + cellsort_bytes(sim) + tiled_bytes(sim);
+    if (sim->engine == PSIM_ENGINE_TILED) tiled_info(sim, out);
+    return PSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// psim_internal.h -- host-side structures shared by the engines and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/psim.h"
+
+namespace psim {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+
+#define PSIM_CUDA(call)                                                                                 \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return ::psim::fail(PSIM_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                                __LINE__);                                                              \
+    } while (0)
+
+#define PSIM_TRY(expr)                 \
+    do {                               \
+        int s__ = (expr);              \
+        if (s__ != PSIM_OK) return s__; \
+    } while (0)
+
+// device error word (sticky, OR-ed bit flags) ----------------------------------------------------
+enum : int {
+    kErrTileOverflow   = 1,   // a tile received more particles than it has slots
+    kErrHaloOverflow   = 2,   // an edge / corner halo list overflowed
+    kErrOutboxOverflow = 4,   // more particles left a tile in one step than its outbox holds
+    kErrSmemOverflow   = 8,   // a tile's working set (own + apron) exceeded the shared-memory staging area
+    kErrLostParticle   = 16,  // a particle moved farther than one tile in one step
+};
+
+// ---- device buffer bookkeeping ---------------------------------------------------------------
+struct DeviceArena {
+    std::vector<void*> ptrs;
+    size_t bytes = 0;
+    template <class T>
+    int alloc(T** p, size_t count) {
+        *p = nullptr;
+        if (count == 0) count = 1;
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+        if (e != cudaSuccess) return fail(PSIM_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        ptrs.push_back(q);
+        bytes += count * sizeof(T);
+        *p = static_cast<T*>(q);
+        return PSIM_OK;
+    }
+    void release() {
+        for (void* q : ptrs) cudaFree(q);
+        ptrs.clear();
+        bytes = 0;
+    }
+};
+
+// Compact structure-of-arrays view of the particles a handle owns (device pointers).
+struct SoAView {
+    double *x = nullptr, *y = nullptr, *vx = nullptr, *vy = nullptr, *ax = nullptr, *ay = nullptr;
+    int* id = nullptr;
+    int n = 0;
+};
+
+// ---- cell binner: counting sort over cutoff cells (psim_cellsort.cu) ----------------------------
+// histogram (atomic) -> single-pass decoupled-look-back exclusive scan -> scatter.
+struct CellBinner {
+    DeviceArena mem;
+    int bincnt = 0;
+    long long ncell = 0;
+    int capacity_n = 0;
+    int* cell_start = nullptr;   // ncell + 1 : counts, then exclusive prefix in place
+    int* slot = nullptr;         // n : rank of a particle inside its cell (arrival order)
+    unsigned long long* scan_desc = nullptr;
+    int* scan_ticket = nullptr;
+    int scan_tiles = 0;
+    long long launches = 0;
+    int init(int bincnt, int capacity_n);
+    // per-cell counts into cell_start[0..ncell) and the arrival rank of every particle into slot
+    int count(const double* x, const double* y, int n, cudaStream_t s);
+    // count + in-place exclusive scan: cell_start[c] = first sorted index of cell c, cell_start[ncell] = n
+    int build(const double* x, const double* y, int n, cudaStream_t s);
+    void release() { mem.release(); }
+};
+
+struct CellsortEngine;
+struct TiledEngine;
+
+}  // namespace psim
+
+struct psim_sim {
+    int engine = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_total = 0;  // records in the caller's array
+    double size = 0;
+    int bincnt = 0;
+    int rank = 0, nranks = 1;
+    int row_begin = 0, row_end = 0;
+    long long steps_done = 0;
+    long long launches = 0;
+    int* d_err = nullptr;  // device error word
+    int* h_err = nullptr;  // pinned mirror
+    psim::DeviceArena mem;
+    psim::CellsortEngine* cs = nullptr;
+    psim::TiledEngine* tiled = nullptr;
+    // scratch for observation calls
+    psim::DeviceArena scratch;
+    void* comm = nullptr;  // ncclComm_t when connected
+};
+
+namespace psim {
+
+// engines (each returns PSIM_* status)
+int cellsort_create(psim_sim* sim, const particle_t* d_parts_aos, int n);
+int cellsort_step(psim_sim* sim, int nsteps, int flags);
+int cellsort_view(psim_sim* sim, SoAView* out);  // current compact state
+void cellsort_destroy(psim_sim* sim);
+long long cellsort_bytes(psim_sim* sim);
+
+int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts, int n, bool parts_on_device,
+                 bool* unsuitable);
+int tiled_exchange(psim_sim* sim, int parity, cudaStream_t s);  // psim_comm.cpp
+void tiled_boundary_rows(psim_sim* sim, int parity, char** first_owned, char** last_owned, char** ghost_lo, char** ghost_hi,
+                         size_t* row_bytes);
+void comm_destroy(psim_sim* sim);
+int tiled_step(psim_sim* sim, int nsteps, int flags);
+int tiled_view(psim_sim* sim, SoAView* out);  // gathers into scratch
+void tiled_destroy(psim_sim* sim);
+long long tiled_bytes(psim_sim* sim);
+void tiled_info(psim_sim* sim, psim_info_t* out);
+
+}  // namespace psim

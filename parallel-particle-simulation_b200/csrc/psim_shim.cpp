@@ -1,0 +1,104 @@
+// psim_shim.cpp -- the drop-in: exports the reference's two C++-linkage entry points
+//     void init_simulation(particle_t*, int, double)      _Z15init_simulationP10particle_tid
+//     void simulate_one_step(particle_t*, int, double)    _Z17simulate_one_stepP10particle_tid
+// (reference part1/common.h:24-25) on top of the C ABI of libpsim, so that the reference's own
+// drivers link against this library unmodified:
+//   * part1/main.cpp (serial build)   -- host pointer, one calling thread
+//   * part1/main.cpp (OpenMP build)   -- host pointer, EVERY thread of the parallel region calls
+//                                        simulate_one_step each step (main.cpp:124-129)
+//   * part3/main.cu                   -- device pointer (cudaMalloc'ed AoS), one calling thread
+//
+// Observable contract: after call k returns, parts[i] holds the state after
+// step k in original order.  The drivers read `parts` only when (k % savefreq) == 0
+// (main.cpp:135-136, main.cu:134-136), so the default policy writes the caller's array back on
+// exactly those calls and on the last one (k == nsteps-1); PSIM_SYNC=every restores the literal
+// every-call write-back, PSIM_SYNC=final only the last, PSIM_SYNC=none never.
+//
+// Errors: the reference has no error channel; its CUDA part prints "GPUassert: <msg> <file> <line>"
+// to stderr and exits (part3/gpu.cu:70-77).  Any non-zero libpsim status does the same here.
+//
+// Environment: PSIM_ENGINE=auto|cellsort|tiled  PSIM_TILE=16|32|64  PSIM_DEVICE=<ordinal>
+//              PSIM_SYNC=save|every|final|none   PSIM_VERBOSE=1
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/psim.h"
+
+namespace {
+
+psim_sim* g_sim = nullptr;
+long long g_call = 0;
+enum Policy { kSave, kEvery, kFinal, kNone } g_policy = kSave;
+
+[[noreturn]] void die(int status, const char* file, int line) {
+    std::fprintf(stderr, "GPUassert: %s: %s %s %d\n", psim_error_string(status), psim_last_error(), file, line);
+    std::exit(status);
+}
+#define SHIM_CHECK(call)                         \
+    do {                                         \
+        int st__ = (call);                       \
+        if (st__ != PSIM_OK) die(st__, __FILE__, __LINE__); \
+    } while (0)
+
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+void step_once(particle_t* parts) {
+    const long long k = g_call++;
+    bool materialise = false;
+    switch (g_policy) {
+        case kEvery: materialise = true; break;
+        case kSave: materialise = (k % PSIM_SAVEFREQ) == 0 || k == PSIM_NSTEPS - 1; break;
+        case kFinal: materialise = k == PSIM_NSTEPS - 1; break;
+        case kNone: break;
+    }
+    SHIM_CHECK(psim_step(g_sim, 1, materialise ? PSIM_STEP_DEFAULT : PSIM_STEP_ACCEL_NONE));
+    if (materialise) SHIM_CHECK(psim_read_particles(g_sim, parts));
+}
+
+}  // namespace
+
+void init_simulation(particle_t* parts, int num_parts, double size) {
+    psim_config cfg;
+    psim_config_default(&cfg);
+    if (const char* e = std::getenv("PSIM_ENGINE")) {
+        if (!std::strcmp(e, "cellsort")) cfg.engine = PSIM_ENGINE_CELLSORT;
+        else if (!std::strcmp(e, "tiled")) cfg.engine = PSIM_ENGINE_TILED;
+    }
+    cfg.tile_cells = env_int("PSIM_TILE", 0);
+    cfg.device = env_int("PSIM_DEVICE", -1);
+    if (const char* p = std::getenv("PSIM_SYNC")) {
+        if (!std::strcmp(p, "every")) g_policy = kEvery;
+        else if (!std::strcmp(p, "final")) g_policy = kFinal;
+        else if (!std::strcmp(p, "none")) g_policy = kNone;
+        else g_policy = kSave;
+    }
+    if (g_sim) {
+        psim_destroy(g_sim);
+        g_sim = nullptr;
+    }
+    g_call = 0;
+    SHIM_CHECK(psim_create(&g_sim, &cfg, parts, num_parts, size));
+    if (env_int("PSIM_VERBOSE", 0)) {
+        psim_info_t info;
+        psim_info(g_sim, &info);
+        std::fprintf(stderr, "[psim] engine=%s device=%d cells/side=%d tile=%d capacity=%d device_bytes=%lld\n",
+                     info.engine == PSIM_ENGINE_TILED ? "tiled" : "cellsort", info.device, info.bin_count, info.tile_cells,
+                     info.tile_capacity, info.device_bytes);
+    }
+}
+
+void simulate_one_step(particle_t* parts, int /*num_parts*/, double /*size*/) {
+    // Under the OpenMP driver the whole team arrives here; one thread drives the GPU and the
+    // others wait.  Outside a parallel region the directives bind to a team of one.
+#pragma omp barrier
+#pragma omp master
+    {
+        if (!g_sim) die(PSIM_ERR_STATE, __FILE__, __LINE__);
+        step_once(parts);
+    }
+#pragma omp barrier
+}

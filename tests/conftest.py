@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    import __graft_entry__ as g
+
+    if not os.path.exists(os.path.join(g.PKG_DIR, "csrc", "build", "libpsim.so")):
+        g.build()
+    return g.load_package()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from psim_testlib import Oracle
+
+    return Oracle()

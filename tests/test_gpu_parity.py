@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, the committed reference
+fixtures (tests/golden/, produced from the unmodified reference by gen_golden.py) and -- where the
+prebuilt files travelled with the snapshot -- the reference kernels themselves (oracle/_ref/).
+
+Tolerances (BASELINE.json north_star): cell ids and per-cell counts bit-exact; positions, velocities
+and accelerations after one step within 1e-12 relative (|d| / max(|ref|, 1)); in practice the CUDA
+arithmetic is non-contracted IEEE double in a canonical summation order, so the tests also assert
+BIT equality wherever the reference's own summation order is reproducible (<= 2 in-range neighbours,
+which is every particle of the fixtures)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from psim_testlib import GOLDEN_DIR, REF_DIR, RefKernel, box_size, have_ref, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["cellsort", "tiled16", "tiled32", "tiled64"]
+
+
+def make_sim(pkg, parts, size, engine):
+    if engine == "cellsort":
+        return pkg.Simulation(parts, len(parts), size, engine=pkg.ENGINE_CELLSORT)
+    return pkg.Simulation(parts, len(parts), size, engine=pkg.ENGINE_TILED, tile_cells=int(engine[5:]))
+
+
+# ---------------------------------------------------------------- binning
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("fixture,step", [("ref_n1000_s1.npz", 0), ("ref_n1000_s1.npz", 100), ("ref_n1000_s1.npz", 1000),
+                                          ("ref_n3000_s7.npz", 200)])
+def test_cells_match_reference_bins_bit_exact(pkg, engine, fixture, step):
+    g = load_golden(fixture)
+    parts, size = g[f"step{step}"].copy(), float(g["size"])
+    sim = make_sim(pkg, parts, size, engine)
+    ids, counts = sim.read_cells()
+    assert pkg.bin_count(size) == int(g["bincnt"])
+    assert np.array_equal(ids, g[f"cellid{step}"])          # the reference's own Bins membership
+    assert np.array_equal(counts, g[f"cellcount{step}"])    # the sizes of the reference's sets
+    sim.close()
+
+
+@pytest.mark.parametrize("engine", ["cellsort", "tiled32"])
+def test_cell_lists_match_oracle(pkg, oracle, engine):
+    n = 20000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 5)
+    oracle.step(parts, size, 40)
+    sim = make_sim(pkg, parts, size, engine)
+    start, members = sim.read_cell_lists()
+    ostart, omembers = oracle.cell_lists(parts, size)
+    assert np.array_equal(start, ostart)
+    # same membership per cell; ours is ordered by original index, the oracle's by (x, y, index)
+    order = np.lexsort((omembers, np.repeat(np.arange(len(ostart) - 1), np.diff(ostart))))
+    assert np.array_equal(members, omembers[order])
+    sim.close()
+
+
+# ---------------------------------------------------------------- one step from a warmed state (a6-a9)
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("fixture,step", [("ref_n1000_s1.npz", 50), ("ref_n3000_s7.npz", 100)])
+def test_one_step_matches_reference(pkg, oracle, engine, fixture, step):
+    g = load_golden(fixture)
+    parts, size = g[f"step{step}"].copy(), float(g["size"])
+    want = g[f"step{step + 1}"]
+    sim = make_sim(pkg, parts, size, engine)
+    got = sim.step(1).sync().read_particles()
+    assert rel_err(got[:, :2], want[:, :2]) <= 1e-12     # positions
+    assert rel_err(got[:, 2:4], want[:, 2:4]) <= 1e-12   # velocities
+    assert rel_err(got[:, 4:], want[:, 4:]) <= 1e-12     # accelerations used by the step
+    assert np.abs(want[:, 4:]).max() > 0                  # the fixture really has interactions
+    assert np.array_equal(got, want), "expected bit equality with the reference for this fixture"
+    sim.close()
+
+
+# ---------------------------------------------------------------- trajectories
+@pytest.mark.parametrize("engine", ENGINES)
+def test_trajectory_1000_steps_bit_identical_to_reference(pkg, engine):
+    """BASELINE configs[0]: -n 1000 -s 1, 1000 steps.  serial.cpp and the canonical order agree bit
+    for bit at this size (no particle ever has three in-range neighbours)."""
+    g = load_golden("ref_n1000_s1.npz")
+    size = float(g["size"])
+    sim = make_sim(pkg, g["step0"].copy(), size, engine)
+    done = 0
+    for mark in (1, 50, 100, 300, 1000):
+        sim.step(mark - done)
+        done = mark
+        got = sim.sync().read_particles()
+        assert np.array_equal(got[:, :4], g[f"step{mark}"][:, :4]), f"diverged by step {mark}"
+        assert np.array_equal(got[:, 4:], g[f"step{mark}"][:, 4:])
+    sim.close()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_short_trajectory_vs_oracle_20k(pkg, oracle, engine):
+    """100 steps at N = 20 000: stated tolerance 1e-12 relative on positions; the canonical summation
+    order makes CUDA and oracle bit-identical, which is asserted too."""
+    n = 20000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 11)
+    oracle.step(parts, size, 30)
+    want = parts.copy()
+    sim = make_sim(pkg, parts, size, engine)
+    oracle.step(want, size, 100)
+    got = sim.step(100).sync().read_particles()
+    assert rel_err(got[:, :4], want[:, :4]) <= 1e-12
+    assert np.array_equal(got, want)
+    sim.close()
+
+
+def test_engines_agree_bitwise_and_with_reference_statistics(pkg, oracle):
+    n = 50000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 42)
+    sims = {e: make_sim(pkg, parts, size, e) for e in ENGINES}
+    states = {e: s.step(300).sync().read_particles() for e, s in sims.items()}
+    for e in ENGINES[1:]:
+        assert np.array_equal(states[e], states["cellsort"]), e
+    want = parts.copy()
+    oracle.step(want, size, 300)
+    assert np.array_equal(states["cellsort"], want)
+    st, ost = sims["tiled32"].stats(), oracle.stats(want, size)
+    assert st["pairs"] == ost["pairs"] and st["touched"] == ost["touched"]
+    assert st["max_neighbours"] == ost["max_neighbours"]
+    assert abs(st["dmin"] - ost["dmin"]) <= 1e-15 and abs(st["davg"] - ost["davg"]) <= 1e-12
+    assert abs(st["kinetic_energy"] - ost["ke"]) <= 1e-9 * ost["ke"]
+    assert abs(st["vmax"] - ost["vmax"]) <= 1e-12
+    for s in sims.values():
+        s.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_against_live_reference_kernel_100k(pkg):
+    """BASELINE configs[1] size: 100 000 particles, 60 steps, against the unmodified serial.cpp."""
+    n = 100000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 42)
+    ref_state = parts.copy()
+    ref = RefKernel("serial").init(ref_state, size)
+    sim = pkg.Simulation(parts, n, size)
+    ref.step(60)
+    got = sim.step(60).sync().read_particles()
+    assert rel_err(got[:, :4], ref_state[:, :4]) <= 1e-12
+    differing = int((got != ref_state).any(axis=1).sum())
+    assert differing <= 5  # only particles with >= 3 in-range neighbours sharing a cell may differ in the last bit
+    ids, counts = sim.read_cells()
+    if differing == 0:
+        assert np.array_equal(counts, ref.cell_counts())
+    sim.close()
+
+
+# ---------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("engine", ["cellsort", "tiled16"])
+def test_edge_cases(pkg, oracle, engine):
+    size = box_size(1000)
+    cases = {
+        "single": np.array([[0.3, 0.3, 0.5, -0.25, 0, 0]]),
+        "pair_in_range": np.array([[0.300, 0.300, 0, 0, 0, 0], [0.305, 0.302, 0, 0, 0, 0]]),
+        "pair_closer_than_min_r": np.array([[0.30, 0.30, 0, 0, 0, 0], [0.30000001, 0.30, 0, 0, 0, 0]]),
+        "coincident": np.array([[0.30, 0.30, 0.1, 0, 0, 0], [0.30, 0.30, -0.1, 0, 0, 0]]),
+        "wall_bounce": np.array([[1e-5, size - 1e-5, -1.0, 1.0, 0, 0], [size - 1e-6, 2e-6, 3.0, -2.5, 0, 0]]),
+        "four_body": np.array([[0.40, 0.40, 0, 0, 0, 0], [0.405, 0.40, 0, 0, 0, 0], [0.40, 0.406, 0, 0, 0, 0],
+                               [0.396, 0.397, 0, 0, 0, 0], [0.4041, 0.4043, 0, 0, 0, 0]]),
+        "cell_boundary": np.array([[0.07, 0.29, 0, 0, 0, 0], [0.58, 0.57, 0, 0, 0, 0], [0.0, 0.0, 0, 0, 0, 0]]),
+    }
+    for name, parts in cases.items():
+        parts = np.ascontiguousarray(parts, dtype=np.float64)
+        want = parts.copy()
+        sim = make_sim(pkg, parts, size, engine)
+        ids, counts = sim.read_cells()
+        assert np.array_equal(ids, oracle.cell_ids(parts, size)), name
+        assert np.array_equal(counts, oracle.cell_counts(parts, size)), name
+        for _ in range(5):
+            oracle.step(want, size, 1)
+            got = sim.step(1).sync().read_particles()
+            assert np.array_equal(got, want), name
+        sim.close()
+
+
+def test_empty_and_dense_inputs(pkg, oracle):
+    sim = pkg.Simulation(np.zeros((0, 6)), 0, 0.5)
+    sim.step(3).sync()
+    assert sim.read_particles().shape == (0, 6)
+    sim.close()
+    # 600 particles inside one tile: the tiled engine refuses, AUTO falls back to cellsort and matches
+    rng = np.random.default_rng(0)
+    n, size = 600, box_size(1000)
+    parts = np.zeros((n, 6))
+    parts[:, 0] = 0.2 + 0.1 * rng.random(n)
+    parts[:, 1] = 0.2 + 0.1 * rng.random(n)
+    with pytest.raises(pkg.PsimError) as ei:
+        pkg.Simulation(parts, n, size, engine=pkg.ENGINE_TILED, tile_cells=16)
+    assert ei.value.status == 7
+    sim = pkg.Simulation(parts, n, size)
+    assert sim.info()["engine"] == pkg.ENGINE_CELLSORT
+    want = parts.copy()
+    oracle.step(want, size, 3)
+    got = sim.step(3).sync().read_particles()
+    assert rel_err(got[:, :4], want[:, :4]) <= 1e-12 and np.array_equal(got, want)
+    sim.close()
+
+
+def test_device_pointer_flavour(pkg, oracle):
+    """part3/main.cu hands init_simulation a cudaMalloc'ed AoS; read-back into a device array too."""
+    import torch
+
+    n = 5000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 2)
+    oracle.step(parts, size, 40)
+    dev = torch.from_numpy(parts).cuda()
+    sim = pkg.Simulation(dev, n, size)
+    sim.step(7).sync()
+    out = torch.zeros_like(dev)
+    sim.read_particles(out)
+    want = parts.copy()
+    oracle.step(want, size, 7)
+    assert np.array_equal(out.cpu().numpy(), want)
+    sim.close()
+
+
+# ---------------------------------------------------------------- drop-in drivers
+def _trajectory_md5(cmd, tmp_path, env=None):
+    out = tmp_path / "traj.txt"
+    e = dict(os.environ)
+    e.update(env or {})
+    res = subprocess.run(cmd + ["-n", "1000", "-s", "1", "-o", str(out)], capture_output=True, text=True, env=e, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.startswith("Simulation Time = ") and res.stdout.rstrip().endswith("seconds for 1000 particles.")
+    return hashlib.md5(out.read_bytes()).hexdigest()
+
+
+def test_own_driver_reproduces_reference_trajectory_file(pkg, tmp_path):
+    want = json.load(open(os.path.join(GOLDEN_DIR, "ref_trajectory_n1000_s1.json")))["md5"]
+    drv = os.path.join(os.path.dirname(pkg.lib_path()), "psim")
+    assert _trajectory_md5([drv], tmp_path) == want
+    assert _trajectory_md5([drv], tmp_path, {"PSIM_ENGINE": "cellsort"}) == want
+
+
+@pytest.mark.parametrize("driver", ["dropin_serial_driver", "dropin_openmp_driver", "dropin_gpu_driver"])
+def test_reference_drivers_linked_against_shim(driver, tmp_path):
+    """The reference's UNMODIFIED main.cpp / main.cu, linked against libpsim_shim.so instead of the
+    reference kernels, must write the same trajectory file as the stock serial binary."""
+    path = os.path.join(REF_DIR, driver)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref drop-in drivers not built")
+    want = json.load(open(os.path.join(GOLDEN_DIR, "ref_trajectory_n1000_s1.json")))["md5"]
+    assert _trajectory_md5([path], tmp_path, {"OMP_NUM_THREADS": "4"}) == want
