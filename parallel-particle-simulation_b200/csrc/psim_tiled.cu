@@ -786,7 +786,7 @@ int tiled_step(psim_sim* sim, int nsteps, int flags) {
 int tiled_view(psim_sim* sim, SoAView* out) {
     TiledEngine* e = sim->tiled;
     cudaStream_t s = sim->stream;
-    if (e->g_capacity < sim->n_total) {
+    if (!e->g_cursor || e->g_capacity < sim->n_total) {
         e->gmem.release();
         const size_t c = (size_t)sim->n_total + 2;
         PSIM_TRY(e->gmem.alloc(&e->g.x, c));
