@@ -94,6 +94,10 @@ typedef struct psim_info_t {
     long long steps_done;
     long long kernel_launches; /* kernels this handle launched so far                           */
     long long device_bytes;    /* device memory held                                            */
+    /* tiled engine, as of the last psim_sync / observation call: high-water marks against the
+     * fixed capacities (outbox records per tile-step, edge halo list length, tile population, apron) */
+    int hw_leavers, hw_halo_list, hw_tile_population, hw_apron;
+    int outbox_capacity, halo_list_capacity;
 } psim_info_t;
 
 /* ---- errors ---- */

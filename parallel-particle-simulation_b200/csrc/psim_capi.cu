@@ -195,13 +195,17 @@ static int view_of(psim_sim* sim, SoAView* v, bool* have_acc) {
 }
 
 static int check_device_error(psim_sim* sim) {
-    PSIM_CUDA(cudaMemcpyAsync(sim->h_err, sim->d_err, sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+    PSIM_CUDA(cudaMemcpyAsync(sim->h_err, sim->d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
     PSIM_CUDA(cudaStreamSynchronize(sim->stream));
     const int e = *sim->h_err;
     if (e == 0) return PSIM_OK;
-    return fail(PSIM_ERR_CAPACITY, "device capacity error 0x%x:%s%s%s%s%s", e, (e & kErrTileOverflow) ? " tile-overflow" : "",
-                (e & kErrHaloOverflow) ? " halo-list-overflow" : "", (e & kErrOutboxOverflow) ? " outbox-overflow" : "",
-                (e & kErrSmemOverflow) ? " apron-staging-overflow" : "", (e & kErrLostParticle) ? " particle-skipped-a-tile" : "");
+    return fail(PSIM_ERR_CAPACITY,
+                "device capacity error 0x%x:%s%s%s%s%s (high-water marks: leavers/tile-step %d, edge halo list %d, tile population "
+                "%d, apron %d)",
+                e, (e & kErrTileOverflow) ? " tile-overflow" : "", (e & kErrHaloOverflow) ? " halo-list-overflow" : "",
+                (e & kErrOutboxOverflow) ? " outbox-overflow" : "", (e & kErrSmemOverflow) ? " apron-staging-overflow" : "",
+                (e & kErrLostParticle) ? " particle-skipped-a-tile" : "", sim->h_err[1], sim->h_err[2], sim->h_err[3],
+                sim->h_err[4]);
 }
 
 struct DeviceGuard {
@@ -294,10 +298,10 @@ int psim_create(psim_sim** out, const psim_config* cfg_in, const particle_t* par
         if (e != cudaSuccess) return bail(fail(PSIM_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
         sim->own_stream = true;
     }
-    int st = sim->mem.alloc(&sim->d_err, 4);
+    int st = sim->mem.alloc(&sim->d_err, 8);
     if (st) return bail(st);
-    if (cudaMemsetAsync(sim->d_err, 0, 4 * sizeof(int), sim->stream) != cudaSuccess ||
-        cudaHostAlloc(&sim->h_err, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+    if (cudaMemsetAsync(sim->d_err, 0, 8 * sizeof(int), sim->stream) != cudaSuccess ||
+        cudaHostAlloc(&sim->h_err, 8 * sizeof(int), cudaHostAllocDefault) != cudaSuccess)
         return bail(fail(PSIM_ERR_CUDA, "psim_create: error-word allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
 
     const bool on_device = num_parts > 0 && pointer_on_device(parts);
@@ -578,7 +582,13 @@ int psim_info(psim_sim* sim, psim_info_t* out) {
     out->kernel_launches = sim->launches;
     out->num_parts = sim->n_total;
     out->device_bytes = (long long)sim->mem.bytes + cellsort_bytes(sim) + tiled_bytes(sim);
-    if (sim->engine == PSIM_ENGINE_TILED) tiled_info(sim, out);
+    if (sim->engine == PSIM_ENGINE_TILED) {
+        tiled_info(sim, out);
+        out->hw_leavers = sim->h_err[1];
+        out->hw_halo_list = sim->h_err[2];
+        out->hw_tile_population = sim->h_err[3];
+        out->hw_apron = sim->h_err[4];
+    }
     return PSIM_OK;
 }
 

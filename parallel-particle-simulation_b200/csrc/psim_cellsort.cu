@@ -170,14 +170,12 @@ __global__ void __launch_bounds__(kThreads) force_move_cells_kernel(
             k1[dr + 1] = __ldg(cell_start + b + c_hi + 1);
         }
     }
-    auto visit = [&](auto&& f, bool want_rank) {
-#pragma unroll
+    auto visit = [&](auto&& f) {
+#pragma unroll 1
         for (int dr = -1; dr <= 1; ++dr) {
             for (int k = k0[dr + 1]; k < k1[dr + 1]; ++k) {
                 const double xj = __ldg(x + k), yj = __ldg(y + k);
-                int rank = 0;
-                if (want_rank) rank = visit_rank(dr, axis_cell(yj, bincnt) - col);
-                f(xj, yj, rank);
+                f(xj, yj, visit_rank(dr, axis_cell(yj, bincnt) - col));
             }
         }
     };

@@ -23,8 +23,17 @@ constexpr double kBin     = PSIM_BIN_SIZE;
 // (reference part1/serial.cpp:41-42; v*100.0 is NOT bit-identical).  Clamped to [0, bincnt-1]:
 // the reference indexes out of bounds for v == size when size/0.01 is an integer (e.g. 20 M
 // particles, size == 100.0); that state is unreachable in practice, the clamp only keeps memory safe.
+static __device__ __noinline__ int axis_cell_divide(double v) { return __double2int_rd(__ddiv_rn(v, kBin)); }
+
+// Fast exact evaluation.  t = RN(v * 100) differs from the real quotient q = v / 0.01 by less than
+// |q| * 1.4e-16 (0.01 is 2.1e-17 relative above 1/100, plus one rounding), and so does RN(q).  Unless
+// t lies within 1e-9 of an integer, floor(t) == floor(RN(q)) for every |q| < 1e6 (error < 1.4e-10);
+// the rare values that close to a cell edge (and v == 0, -0) take the true division.
 __device__ __forceinline__ int axis_cell(double v, int bincnt) {
-    int c = __double2int_rd(__ddiv_rn(v, kBin));
+    const double t = __dmul_rn(v, 100.0);
+    int c = __double2int_rd(t);
+    const double f = __dsub_rn(t, __int2double_rn(c));
+    if (f < 1e-9 || f > 1.0 - 1e-9) c = axis_cell_divide(v);
     return min(max(c, 0), bincnt - 1);
 }
 

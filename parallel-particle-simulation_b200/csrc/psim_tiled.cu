@@ -1,26 +1,33 @@
 // psim_tiled.cu -- the "tiled" engine: persistent tile-resident particles, one fused kernel per step.
 //
-// Layout in HBM.  The box is cut into square tiles of TS x TS cutoff cells.  Every tile owns CAP
-// particle slots in five structure-of-arrays streams (x, y, vx, vy, id; plus ax, ay written only on
-// steps whose accelerations are kept).  A tile's live particles occupy slots [0, count) of its
-// stripe, so one CTA streams its tile with fully coalesced 8-byte-per-lane loads and stores and the
-// steady-state HBM traffic is read 32 B + write 32 B per particle-step plus a few percent of
-// boundary lists -- there is no global histogram, scan or scatter in the time loop.
+// Layout in HBM.  The box is cut into square tiles of TS x TS cutoff cells.  Every tile owns a stripe
+// of CAP particle slots in five structure-of-arrays streams (x, y, vx, vy, id; plus ax, ay written
+// only on steps whose accelerations are kept).  A tile's live particles occupy slots [0, count) and a
+// particle keeps its slot for as long as it stays in the tile.  Steady-state HBM traffic is therefore
+// read 32 B + write 32 B per particle-step plus a few percent of boundary lists: there is no global
+// histogram, scan or scatter in the time loop.
 //
-// Per step, CTA = tile (kernel tile_step_kernel):
-//   A. load own particles; ingest particles that entered the tile during the previous step from the
-//      9 surrounding "outboxes"; load the one-cell apron around the tile from the neighbours'
-//      edge / corner "halo lists" (and from outbox entries that sit in the apron)
-//   B. bin own + apron particles into (TS+2)^2 cutoff cells IN SHARED MEMORY (atomic count,
-//      block scan, index scatter) -- reference part3/gpu.cu:92-112 does this in global memory
-//   C. force: every own particle walks its 3x3 cells = three contiguous shared-memory index
-//      ranges (reference part1/serial.cpp:102-117, 19-36), canonical summation order
+// Per step one persistent kernel (tile_step_kernel); a CTA walks tiles blockIdx.x, +gridDim.x, ...
+// with a two-stage shared-memory pipeline fed by TMA bulk copies (cp.async.bulk + mbarrier):
+//   while tile k is computed, the bulk copies of tile k+1 (its 5 stripes, the 8 neighbour halo lists
+//   and the 9 surrounding outboxes) are in flight and the list counts of tile k+2 are being fetched,
+//   so no warp ever waits on a dependent chain of global loads.
+// Compute on a staged tile:
+//   A. ingest: particles that entered the tile last step (outbox records of the 3x3 tiles) are
+//      appended; the one-cell apron is assembled from the neighbours' edge / corner halo lists (and
+//      from outbox records that sit in the apron)
+//   B. bin own + apron particles into a (TS+2)^2 table IN SHARED MEMORY: per cutoff cell a
+//      population word and up to four particle indices (one atomicAdd + one 16-bit store per particle;
+//      reference part3/gpu.cu:92-112 does this in global memory with 16 slots per cell)
+//   C. force: every own particle reads the 9 words of its 3x3 neighbourhood (reference
+//      part1/serial.cpp:102-117, 19-36), canonical summation order; cells with more than four
+//      particles switch the tile to an exact all-pairs sweep
 //   D. move + reflect (reference part1/serial.cpp:46-61) in registers
-//   E. re-tile: particles still in the tile are compacted back into the tile's stripe (in place);
-//      leavers go to the tile's outbox; particles now in the tile's boundary cells are appended to
-//      the edge / corner halo lists the neighbours will read next step.
-// Halo lists and outboxes ("exports") are double buffered by step parity, so a step reads parity p
-// and writes parity p^1 and no CTA ever reads data another CTA of the same launch writes.
+//   E. re-tile: stayers are written back to their own slot, leavers go to the tile's outbox and the
+//      holes they leave are filled from the tail; particles in the tile's boundary cells are
+//      appended to the edge / corner halo lists the neighbours read next step.
+// Halo lists and outboxes ("exports") are double buffered by step parity: a step reads parity p and
+// writes parity p^1, so no CTA ever reads what another CTA of the same launch writes.
 //
 // Slabs (precedent reference part2/mpi.cpp:258-270,296-365): a rank owns a
 // contiguous range of tile rows plus one ghost tile row on each side that holds only exports.  The
@@ -38,20 +45,62 @@ namespace psim {
 // ------------------------------------------------------------------------------------------
 // compile-time tile configurations
 // ------------------------------------------------------------------------------------------
+// CAP slots per tile (mean population is 0.2*TS^2), HE / HC entries per edge / corner halo list,
+// CO outbox records per tile of which the first CS are staged in shared memory by the pipeline (a
+// tile that receives more from one neighbour reads the rest straight from global memory: this only
+// happens in bursts, e.g. a column of the initial lattice that sits exactly on a tile boundary),
+// THREADS per CTA (each thread owns PER = CAP/THREADS slots), CTAS resident per SM.
 template <int TS> struct TileCfg;
-template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 16, THREADS = 64;  };
-template <> struct TileCfg<32> { static constexpr int CAP = 384,  HE = 40, HC = 8, CO = 32, THREADS = 256; };
-template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 48, THREADS = 512; };
+// THREADS are the CONSUMER threads; every CTA has one more warp, the producer, that only feeds the pipeline.
+template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 64, CS = 4,  THREADS = 128, CTAS = 6; };
+template <> struct TileCfg<32> { static constexpr int CAP = 352,  HE = 32, HC = 8, CO = 64, CS = 8,  THREADS = 352, CTAS = 3; };
+template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 64, CS = 16, THREADS = 576, CTAS = 1; };
+
+struct __align__(16) OutRec {  // one migrating particle, 64 bytes
+    double x, y, vx, vy, ax, ay;
+    int id;
+    int pad[3];
+};
+static_assert(sizeof(OutRec) == 64, "OutRec must be 64 bytes");
 
 template <int TS> struct TileDims {
     using C = TileCfg<TS>;
     static constexpr int W = TS + 2, NC = W * W;
-    static constexpr int MAXH = 4 * C::HE + 4 * C::HC + 32;
+    static constexpr int HL = 4 * C::HE + 4 * C::HC;      // halo entries a tile exports / stages
+    static constexpr int MAXH = HL + 32;                  // apron capacity (halo lists + apron outbox records)
     static constexpr int PTOT = C::CAP + MAXH;
-    static constexpr int PER = (C::CAP + C::THREADS - 1) / C::THREADS;
-    static constexpr int HL = 4 * C::HE + 4 * C::HC;  // halo entries per tile
-    static constexpr size_t smem_bytes =
-        sizeof(double) * (2 * PTOT + 2 * C::CAP) + sizeof(int) * (C::CAP + NC + 4) + sizeof(unsigned short) * (3 * PTOT + 8);
+    static constexpr int PER = C::CAP / C::THREADS;
+    static constexpr int LMAX = C::CO;                    // leaver list capacity
+    static_assert(C::CAP % C::THREADS == 0 && C::CAP % 4 == 0 && PTOT % 2 == 0, "alignment");
+};
+
+// one pipeline stage in shared memory (TMA destinations first, 16-byte aligned)
+template <int TS> struct __align__(16) Stage {
+    using C = TileCfg<TS>;
+    using D = TileDims<TS>;
+    double x[D::PTOT], y[D::PTOT];   // own [0, n) then apron [CAP, CAP + n_apron)
+    double vx[C::CAP], vy[C::CAP];
+    int id[C::CAP];
+    double2 halo[D::HL];             // raw halo lists of the 8 neighbours
+    OutRec obox[9][C::CS];           // first CS records of the outboxes of the 3x3 tiles
+};
+
+template <int TS> struct __align__(16) TileSmem {
+    using C = TileCfg<TS>;
+    using D = TileDims<TS>;
+    Stage<TS> st[2];
+    unsigned long long cell_idx[D::NC];       // per cell: up to four particle indices (16 bits each, plain stores)
+    unsigned cell_cnt[D::NC];                 // per cell: population (touched by atomics only)
+    unsigned long long full[2];               // mbarriers: stage filled by TMA (producer -> consumers)
+    unsigned long long empty[2];              // mbarriers: stage released (consumers -> producer)
+    unsigned short pcell[D::PTOT];
+    int cnts[2][20];                          // list counts of the staged tiles: [0] own, [1..8] halo, [9..17] outbox
+    int leave[D::LMAX];                       // slots of the particles that leave this step
+    int hole_dst[D::LMAX];                    // destination slot of the tail stayers that fill holes
+    int hole[D::LMAX];
+    int n_own, n_apron, n_leave, flags, overflow;
+    int hw_leave, hw_halo, hw_tile, hw_apron;   // high-water marks over the tiles this CTA processed
+    int hout[8];
 };
 
 __host__ __device__ inline int halo_offset(int list, int HE, int HC) { return list < 4 ? list * HE : 4 * HE + (list - 4) * HC; }
@@ -64,9 +113,10 @@ struct TileParams {
     const char* exp_in;
     char* exp_out;
     ExportLayout L;
-    int ntx, nty;   // tiles per side (global)
-    int tr_base;    // global tile row of local row 0
-    int lrow0;      // first local tile row of this launch
+    int ntx, nty;    // tiles per side (global)
+    int tr_base;     // global tile row of local row 0
+    int lrow0;       // first local tile row of this launch
+    int ntiles;      // tiles of this launch (rows * ntx)
     int bincnt;
     double size;
     int* err;
@@ -79,135 +129,214 @@ __device__ __forceinline__ char* row_ptr(char* base, const ExportLayout& L, int 
     return base + (size_t)lrow * L.row_bytes;
 }
 
-// which list of which neighbour feeds my apron: k = 0..7
-//   k: 0 N-neighbour's S list | 1 S-neighbour's N list | 2 W-neighbour's E list | 3 E-neighbour's W list
+// Apron source k = 0..7: which neighbour (dr, dc) and which of ITS lists faces this tile.
+//   k: 0 N-neighbour's S list | 1 S-neighbour's N | 2 W-neighbour's E | 3 E-neighbour's W
 //      4 NW-neighbour's SE corner | 5 NE's SW | 6 SW's NE | 7 SE's NW
-// list ids: 0 N, 1 S, 2 W, 3 E, 4 NW, 5 NE, 6 SW, 7 SE
+// list ids: 0 N, 1 S, 2 W, 3 E, 4 NW, 5 NE, 6 SW, 7 SE (N = row 0 of the tile, W = column 0)
 __device__ __forceinline__ void halo_source(int k, int& dr, int& dc, int& list) {
-    const int drs[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-    const int dcs[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-    const int lists[8] = {1, 0, 3, 2, 7, 6, 5, 4};
-    dr = drs[k];
-    dc = dcs[k];
-    list = lists[k];
+    // packed tables, 4 bits per entry: dr+1, dc+1, list
+    dr = (int)((0x22001120u >> (4 * k)) & 0xF) - 1;    // k0..7: -1 1 0 0 -1 -1 1 1  -> +1: 0 2 1 1 0 0 2 2
+    dc = (int)((0x20202011u >> (4 * k)) & 0xF) - 1;    // k0..7:  0 0 -1 1 -1 1 -1 1 -> +1: 1 1 0 2 0 2 0 2
+    list = (int)((0x45672301u >> (4 * k)) & 0xF);      // k0..7:  1 0 3 2 7 6 5 4
+}
+
+// ---- PTX helpers: mbarrier + 1-D bulk copy (TMA) --------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the consumer threads only (id 1; id 0 is __syncthreads)
+template <int N>
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// tile index of this launch -> local row / column
+struct TileCoord {
+    int lr, tc, tr, lt;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TileParams& P, int t) {
+    TileCoord c;
+    c.lr = P.lrow0 + t / P.ntx;
+    c.tc = t % P.ntx;
+    c.tr = P.tr_base + c.lr;
+    c.lt = c.lr * P.ntx + c.tc;
+    return c;
+}
+
+// list count j of tile t: j = 0 own population, 1..8 apron sources, 9..17 outboxes of the 3x3 tiles
+template <int TS>
+__device__ __forceinline__ int load_count(const TileParams& P, int t, int j) {
+    using C = TileCfg<TS>;
+    const TileCoord c = tile_coord(P, t);
+    if (j == 0) return min(P.tcount[c.lt], C::CAP);
+    int dr, dc, list;
+    if (j <= 8) {
+        halo_source(j - 1, dr, dc, list);
+    } else {
+        dr = (j - 9) / 3 - 1;
+        dc = (j - 9) % 3 - 1;
+        list = 8;
+    }
+    const int ntr = c.tr + dr, ntc = c.tc + dc;
+    if (ntr < 0 || ntr >= P.nty || ntc < 0 || ntc >= P.ntx) return 0;
+    const int* ec = reinterpret_cast<const int*>(row_ptr(P.exp_in, P.L, c.lr + dr) + P.L.off_cnt) + (size_t)ntc * 16;
+    return min(ec[list], list == 8 ? C::CO : halo_cap(list, C::HE, C::HC));
+}
+
+// Issue the bulk copies of tile t into `st` (one warp; lane j owns copy j).
+//   lanes 0-3: x y vx vy stripes, lane 4: id stripe, lanes 5-12: apron sources, lanes 13-21: outboxes
+template <int TS>
+__device__ __forceinline__ void issue_tile_loads(const TileParams& P, int t, Stage<TS>& st, const int* cnt,
+                                                 unsigned long long* bar, int lane) {
+    using C = TileCfg<TS>;
+    using D = TileDims<TS>;
+    const TileCoord c = tile_coord(P, t);
+    const size_t gbase = (size_t)c.lt * C::CAP;
+    const void* src = nullptr;
+    void* dst = nullptr;
+    unsigned bytes = 0;
+    if (lane < 5) {
+        const int n = cnt[0];
+        if (lane < 4) {
+            bytes = (unsigned)((n + 1) >> 1) * 16u;
+            src = (lane == 0 ? P.sx : lane == 1 ? P.sy : lane == 2 ? P.svx : P.svy) + gbase;
+            dst = lane == 0 ? st.x : lane == 1 ? st.y : lane == 2 ? st.vx : st.vy;
+        } else {
+            bytes = (unsigned)((n + 3) >> 2) * 16u;
+            src = P.sid + gbase;
+            dst = st.id;
+        }
+    } else if (lane < 13) {
+        const int k = lane - 5;
+        int dr, dc, list;
+        halo_source(k, dr, dc, list);
+        bytes = (unsigned)cnt[1 + k] * 16u;
+        if (bytes) {
+            src = reinterpret_cast<const double2*>(row_ptr(P.exp_in, P.L, c.lr + dr) + P.L.off_hxy) +
+                  (size_t)(c.tc + dc) * D::HL + halo_offset(list, C::HE, C::HC);
+            dst = st.halo + halo_offset(k, C::HE, C::HC);
+        }
+    } else if (lane < 22) {
+        const int nb = lane - 13;
+        const int dr = nb / 3 - 1, dc = nb % 3 - 1;
+        bytes = (unsigned)min(cnt[9 + nb], C::CS) * (unsigned)sizeof(OutRec);
+        if (bytes) {
+            src = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, c.lr + dr) + P.L.off_obox) + (size_t)(c.tc + dc) * C::CO;
+            dst = st.obox[nb];
+        }
+    }
+    unsigned total = bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) mbar_arrive_expect_tx(bar, total);
+    __syncwarp();
+    if (bytes) tma_load_1d(dst, src, bytes, bar);
 }
 
 // ------------------------------------------------------------------------------------------
 // the per-step kernel
 // ------------------------------------------------------------------------------------------
 template <int TS, bool kStoreAcc>
-__global__ void __launch_bounds__(TileCfg<TS>::THREADS) tile_step_kernel(const TileParams P) {
+__global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) tile_step_kernel(const TileParams P) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, NC = D::NC, PTOT = D::PTOT, PER = D::PER;
-    constexpr int HE = C::HE, HC = C::HC, CO = C::CO;
+    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, NC = D::NC, PER = D::PER;
+    constexpr int HE = C::HE, HC = C::HC, CO = C::CO, LMAX = D::LMAX;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* px = reinterpret_cast<double*>(smem_raw);
-    double* py = px + PTOT;
-    double* pvx = py + PTOT;
-    double* pvy = pvx + CAP;
-    int* pid = reinterpret_cast<int*>(pvy + CAP);
-    int* ccnt = pid + CAP;  // NC + 1 (+3 pad)
-    unsigned short* pcell = reinterpret_cast<unsigned short*>(ccnt + NC + 4);
-    unsigned short* pslot = pcell + PTOT;
-    unsigned short* sidx = pslot + PTOT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileSmem<TS>& S = *reinterpret_cast<TileSmem<TS>*>(smem_raw);
 
-    __shared__ int s_cnt[17];   // 0..7 halo list counts, 8..16 outbox counts of the 3x3 tiles
-    __shared__ int s_hoff[9];
-    __shared__ int s_warp[33];
-    __shared__ int s_nown, s_nhalo, s_flags;
-    __shared__ int s_hout[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int first = blockIdx.x;
+    if (first >= P.ntiles) return;
 
-    const int tid = threadIdx.x;
-    const int lr = P.lrow0 + blockIdx.x / P.ntx, tc = blockIdx.x % P.ntx;
-    const int tr = P.tr_base + lr;
-    const int lt = lr * P.ntx + tc;
-    const int r0 = tr * TS, c0 = tc * TS;
-    const size_t gbase = (size_t)lt * CAP;
-    const int n_own0 = min(P.tcount[lt], CAP);
-
-    // ---- A0: list counts --------------------------------------------------------------------
-    if (tid < 32) {
-        int cnt = 0;
-        if (tid < 17) {
-            int dr, dc, list;
-            if (tid < 8) {
-                halo_source(tid, dr, dc, list);
-            } else {
-                dr = (tid - 8) / 3 - 1;
-                dc = (tid - 8) % 3 - 1;
-                list = 8;
-            }
-            const int ntr = tr + dr, ntc = tc + dc;
-            if (ntr >= 0 && ntr < P.nty && ntc >= 0 && ntc < P.ntx) {
-                const int* ec = reinterpret_cast<const int*>(row_ptr(P.exp_in, P.L, lr + dr) + P.L.off_cnt) + (size_t)ntc * 16;
-                cnt = ec[list];
-                cnt = min(cnt, list == 8 ? CO : halo_cap(list, HE, HC));
-            }
-            s_cnt[tid] = cnt;
-        }
-        int inc = tid < 8 ? cnt : 0;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (tid >= o) inc += t;
-        }
-        if (tid < 8) s_hoff[tid] = inc - cnt;
-        if (tid == 7) s_hoff[8] = inc;
-        if (tid < 8) s_hout[tid] = 0;
-        if (tid == 0) s_flags = 0;
+    // ---- prologue ---------------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        mbar_init(&S.empty[0], 1);
+        mbar_init(&S.empty[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.n_leave = 0;
+        S.flags = 0;
+        S.overflow = 0;
+        S.hw_leave = S.hw_halo = S.hw_tile = S.hw_apron = 0;
     }
-    // own particles (coalesced)
-    for (int i = tid; i < n_own0; i += T) {
-        px[i] = P.sx[gbase + i];
-        py[i] = P.sy[gbase + i];
-        pvx[i] = P.svx[gbase + i];
-        pvy[i] = P.svy[gbase + i];
-        pid[i] = P.sid[gbase + i];
-    }
+    if (tid < 8) S.hout[tid] = 0;
+    for (int c = tid; c < NC; c += T + 32) S.cell_cnt[c] = 0u;
     __syncthreads();
 
-    // ---- A1: apron from the neighbours' halo lists ---------------------------------------------
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) {
-        const int cnt = s_cnt[k];
-        if (cnt == 0) continue;
-        int dr, dc, list;
-        halo_source(k, dr, dc, list);
-        const double2* src = reinterpret_cast<const double2*>(row_ptr(P.exp_in, P.L, lr + dr) + P.L.off_hxy) +
-                             (size_t)(tc + dc) * D::HL + halo_offset(list, HE, HC);
-        for (int e = tid; e < cnt; e += T) {
-            const double2 q = src[e];
-            const int h = PTOT - 1 - (s_hoff[k] + e);
-            px[h] = q.x;
-            py[h] = q.y;
+    // ---- producer warp: runs up to two tiles ahead of the consumers ----------------------------------
+    if (warp == T / 32) {
+        for (int j = 0;; ++j) {
+            const int t = first + j * G;
+            if (t >= P.ntiles) break;
+            const int c = lane < 18 ? load_count<TS>(P, t, lane) : 0;
+            if (j >= 2) mbar_wait(&S.empty[j & 1], (unsigned)(((j >> 1) - 1) & 1));  // tile j-2 has left the stage
+            if (lane < 18) S.cnts[j & 1][lane] = c;
+            __syncwarp();
+            issue_tile_loads<TS>(P, t, S.st[j & 1], S.cnts[j & 1], &S.full[j & 1], lane);
         }
+        return;
     }
-    // ---- A2: outboxes of the 3x3 tiles (last warp): newcomers -> own, apron dwellers -> halo -------
-    if (tid >= T - 32) {
-        const int lane = tid & 31;
-        const unsigned lt_mask = (1u << lane) - 1u;
-        int n_own = n_own0, n_halo = s_hoff[8], flags = 0;
-#pragma unroll 1
-        for (int nb = 0; nb < 9; ++nb) {
-            const int cnt = s_cnt[8 + nb];
-            if (cnt == 0) continue;
-            const int dr = nb / 3 - 1, dc = nb % 3 - 1;
-            const char* row = row_ptr(P.exp_in, P.L, lr + dr);
-            const size_t ob = (size_t)(tc + dc) * CO;
-            const double* ox = reinterpret_cast<const double*>(row + P.L.off_ox) + ob;
-            const double* oy = reinterpret_cast<const double*>(row + P.L.off_oy) + ob;
-            const double* ovx = reinterpret_cast<const double*>(row + P.L.off_ovx) + ob;
-            const double* ovy = reinterpret_cast<const double*>(row + P.L.off_ovy) + ob;
-            const int* oid = reinterpret_cast<const int*>(row + P.L.off_oid) + ob;
-            for (int e0 = 0; e0 < cnt; e0 += 32) {
-                const int e = e0 + lane;
+
+    // ---- consumers ----------------------------------------------------------------------------------
+    for (int it = 0;; ++it) {
+        const int t = first + it * G;
+        if (t >= P.ntiles) break;
+        Stage<TS>& st = S.st[it & 1];
+        const int* cnt = S.cnts[it & 1];
+        const TileCoord tc_ = tile_coord(P, t);
+        const int tr = tc_.tr, tc = tc_.tc, lt = tc_.lt, lr = tc_.lr;
+        const int r0 = tr * TS, c0 = tc * TS;
+        const size_t gbase = (size_t)lt * CAP;
+
+        mbar_wait(&S.full[it & 1], (unsigned)((it >> 1) & 1));  // this tile's bytes (and counts) have landed
+
+        const int n_own0 = cnt[0];
+
+        // ---- A: ingest newcomers and assemble the apron ---------------------------------------------
+        int hoff[9];
+        hoff[0] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hoff[k + 1] = hoff[k] + cnt[1 + k];
+        if (warp == 0) {
+            // outbox records of the 3x3 tiles: records now in my tile are appended to my stripe, records in my
+            // apron ring become apron particles (after the halo-list entries).  One lane per staged record.
+            const unsigned lt_mask = (1u << lane) - 1u;
+            int n_own = n_own0, n_ap = hoff[8], flags = 0;
+            auto take = [&](bool valid, const OutRec* rec) {
                 bool mine = false, apron = false;
                 double x = 0, y = 0;
-                if (e < cnt) {
-                    x = ox[e];
-                    y = oy[e];
+                if (valid) {
+                    x = rec->x;
+                    y = rec->y;
                     const int row_c = axis_cell(x, P.bincnt), col_c = axis_cell(y, P.bincnt);
                     mine = row_c / TS == tr && col_c / TS == tc;
                     apron = !mine && row_c >= r0 - 1 && row_c <= r0 + TS && col_c >= c0 - 1 && col_c <= c0 + TS;
@@ -216,198 +345,267 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS) tile_step_kernel(const T
                 if (mine) {
                     const int d = n_own + __popc(mm & lt_mask);
                     if (d < CAP) {
-                        px[d] = x;
-                        py[d] = y;
-                        pvx[d] = ovx[e];
-                        pvy[d] = ovy[e];
-                        pid[d] = oid[e];
+                        st.x[d] = x;
+                        st.y[d] = y;
+                        st.vx[d] = rec->vx;
+                        st.vy[d] = rec->vy;
+                        st.id[d] = rec->id;
                     }
                 }
                 if (apron) {
-                    const int hh = n_halo + __popc(am & lt_mask);
+                    const int hh = n_ap + __popc(am & lt_mask);
                     if (hh < D::MAXH) {
-                        px[PTOT - 1 - hh] = x;
-                        py[PTOT - 1 - hh] = y;
+                        st.x[CAP + hh] = x;
+                        st.y[CAP + hh] = y;
                     }
                 }
                 n_own += __popc(mm);
-                n_halo += __popc(am);
-            }
-        }
-        if (n_own > CAP) { flags |= kErrTileOverflow; n_own = CAP; }
-        if (n_halo > D::MAXH) { flags |= kErrSmemOverflow; n_halo = D::MAXH; }
-        if (lane == 0) {
-            s_nown = n_own;
-            s_nhalo = n_halo;
-            if (flags) atomicOr(&s_flags, flags);
-        }
-    }
-    for (int c = tid; c < NC + 1; c += T) ccnt[c] = 0;
-    __syncthreads();
-    const int n_own = s_nown, n_halo = s_nhalo, n_all = n_own + n_halo;
-
-    // ---- B: bin own + apron particles into (TS+2)^2 cells in shared memory -----------------------
-    for (int q = tid; q < n_all; q += T) {
-        const int i = q < n_own ? q : PTOT - 1 - (q - n_own);
-        const int lrow = axis_cell(px[i], P.bincnt) - r0 + 1, lcol = axis_cell(py[i], P.bincnt) - c0 + 1;
-        if (lrow >= 0 && lrow < W && lcol >= 0 && lcol < W) {
-            const int cell = lrow * W + lcol;
-            pcell[i] = (unsigned short)cell;
-            pslot[i] = (unsigned short)atomicAdd(&ccnt[cell], 1);
-        } else {
-            pcell[i] = 0xFFFFu;  // cannot happen for well-formed exports; keeps the sort safe
-        }
-    }
-    __syncthreads();
-    {
-        constexpr int CHUNK = (NC + T - 1) / T;
-        const int b = tid * CHUNK;
-        int sum = 0;
-#pragma unroll
-        for (int k = 0; k < CHUNK; ++k)
-            if (b + k < NC) sum += ccnt[b + k];
-        int total;
-        int run = block_exclusive_scan(sum, s_warp, total);
-#pragma unroll
-        for (int k = 0; k < CHUNK; ++k)
-            if (b + k < NC) {
-                const int v = ccnt[b + k];
-                ccnt[b + k] = run;
-                run += v;
-            }
-        if (tid == 0) ccnt[NC] = total;
-    }
-    __syncthreads();
-    for (int q = tid; q < n_all; q += T) {
-        const int i = q < n_own ? q : PTOT - 1 - (q - n_own);
-        const unsigned cell = pcell[i];
-        if (cell != 0xFFFFu) sidx[ccnt[cell] + pslot[i]] = (unsigned short)i;
-    }
-    __syncthreads();
-
-    // ---- C + D: force over the 3x3 neighbourhood, then move, all in registers ---------------------
-    double nx[PER], ny[PER], nvx[PER], nvy[PER], nax[PER], nay[PER];
-    int ncellrow[PER], ncellcol[PER];
-#pragma unroll
-    for (int r = 0; r < PER; ++r) {
-        const int i = r * T + tid;
-        nx[r] = ny[r] = nvx[r] = nvy[r] = nax[r] = nay[r] = 0.0;
-        ncellrow[r] = ncellcol[r] = -1;
-        if (i < n_own) {
-            const double xi = px[i], yi = py[i];
-            const int cell = pcell[i];
-            auto visit = [&](auto&& f, bool want_rank) {
-#pragma unroll
-                for (int dr = -1; dr <= 1; ++dr) {
-                    const int b = cell + dr * W;
-                    const int k0 = ccnt[b - 1], k1 = ccnt[b + 2];
-                    for (int k = k0; k < k1; ++k) {
-                        const int j = sidx[k];
-                        int rank = 0;
-                        if (want_rank) rank = visit_rank(dr, (int)pcell[j] - b);
-                        f(px[j], py[j], rank);
-                    }
-                }
+                n_ap += __popc(am);
             };
-            double ax, ay;
-            int nbc;
-            accumulate_force(xi, yi, visit, ax, ay, nbc);
-            double x = xi, y = yi, vx = pvx[i], vy = pvy[i];
-            move_particle(x, y, vx, vy, ax, ay, P.size);
-            nx[r] = x; ny[r] = y; nvx[r] = vx; nvy[r] = vy; nax[r] = ax; nay[r] = ay;
-            ncellrow[r] = axis_cell(x, P.bincnt);
-            ncellcol[r] = axis_cell(y, P.bincnt);
-        }
-    }
-
-    // ---- E: re-tile: compact stayers in place, leavers to the outbox, boundary cells to halo lists --
-    char* orow = row_ptr(P.exp_out, P.L, lr);
-    double2* ohxy = reinterpret_cast<double2*>(orow + P.L.off_hxy) + (size_t)tc * D::HL;
-    const size_t ob = (size_t)tc * CO;
-    double* oox = reinterpret_cast<double*>(orow + P.L.off_ox) + ob;
-    double* ooy = reinterpret_cast<double*>(orow + P.L.off_oy) + ob;
-    double* oovx = reinterpret_cast<double*>(orow + P.L.off_ovx) + ob;
-    double* oovy = reinterpret_cast<double*>(orow + P.L.off_ovy) + ob;
-    double* ooax = reinterpret_cast<double*>(orow + P.L.off_oax) + ob;
-    double* ooay = reinterpret_cast<double*>(orow + P.L.off_oay) + ob;
-    int* ooid = reinterpret_cast<int*>(orow + P.L.off_oid) + ob;
-
-    int stay_base = 0, leave_base = 0, flags = 0;
+            int total_out = 0, beyond = 0;
 #pragma unroll
-    for (int r = 0; r < PER; ++r) {
-        const int i = r * T + tid;
-        const bool active = i < n_own;
-        const int er = ncellrow[r] - r0, ec = ncellcol[r] - c0;
-        const bool stay = active && er >= 0 && er < TS && ec >= 0 && ec < TS;
-        const int code = active ? (stay ? 1 : (1 << 16)) : 0;
-        int total;
-        const int pre = block_exclusive_scan(code, s_warp, total);  // also orders smem reads above vs writes below
-        if (active) {
-            const int myid = pid[i];
-            if (stay) {
-                const int d = stay_base + (pre & 0xFFFF);
-                P.sx[gbase + d] = nx[r];
-                P.sy[gbase + d] = ny[r];
-                P.svx[gbase + d] = nvx[r];
-                P.svy[gbase + d] = nvy[r];
-                if (kStoreAcc) {
-                    P.sax[gbase + d] = nax[r];
-                    P.say[gbase + d] = nay[r];
+            for (int nb = 0; nb < 9; ++nb) {
+                total_out += cnt[9 + nb];
+                beyond |= cnt[9 + nb] > C::CS;
+            }
+            if (total_out > 0) {
+#pragma unroll 1
+                for (int q0 = 0; q0 < 9 * C::CS; q0 += 32) {
+                    const int q = q0 + lane, nb = q / C::CS, e = q % C::CS;
+                    const bool valid = q < 9 * C::CS && e < cnt[9 + min(nb, 8)];
+                    take(valid, &st.obox[min(nb, 8)][e]);
                 }
-                // the id stream only changes where compaction or ingestion moved a particle
-                if (d >= n_own0 || d != i) P.sid[gbase + d] = myid;
-                const bool n_ = er == 0, s_ = er == TS - 1, w_ = ec == 0, e_ = ec == TS - 1;
-                if (n_ | s_ | w_ | e_) {
-                    const double2 q = make_double2(nx[r], ny[r]);
-                    auto put = [&](int list) {
-                        const int idx = atomicAdd(&s_hout[list], 1);
-                        if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
-                    };
-                    if (n_) put(0);
-                    if (s_) put(1);
-                    if (w_) put(2);
-                    if (e_) put(3);
-                    if (n_ && w_) put(4);
-                    if (n_ && e_) put(5);
-                    if (s_ && w_) put(6);
-                    if (s_ && e_) put(7);
-                }
-            } else {
-                const int d = leave_base + (pre >> 16);
-                if (d < CO) {
-                    oox[d] = nx[r];
-                    ooy[d] = ny[r];
-                    oovx[d] = nvx[r];
-                    oovy[d] = nvy[r];
-                    if (kStoreAcc) {
-                        ooax[d] = nax[r];
-                        ooay[d] = nay[r];
+                if (beyond) {
+                    // bursts only: records past the staged CS are read from the neighbour's outbox in global memory
+#pragma unroll 1
+                    for (int nb = 0; nb < 9; ++nb) {
+                        const int c = cnt[9 + nb];
+                        if (c <= C::CS) continue;
+                        const OutRec* grec = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, lr + nb / 3 - 1) + P.L.off_obox) +
+                                             (size_t)(tc + nb % 3 - 1) * CO;
+                        for (int e0 = C::CS; e0 < c; e0 += 32) take(e0 + lane < c, grec + e0 + lane);
                     }
-                    ooid[d] = myid;
                 }
-                const int dtr = (ncellrow[r] / TS) - tr, dtc = (ncellcol[r] / TS) - tc;
-                if (dtr < -1 || dtr > 1 || dtc < -1 || dtc > 1) flags |= kErrLostParticle;
+            }
+            if (n_own > CAP) { flags |= kErrTileOverflow; n_own = CAP; }
+            if (n_ap > D::MAXH) { flags |= kErrSmemOverflow; n_ap = D::MAXH; }
+            if (lane == 0) {
+                S.n_own = n_own;
+                S.n_apron = n_ap;
+                if (flags) atomicOr(&S.flags, flags);
+            }
+        } else {
+            // halo lists -> contiguous apron positions
+            for (int q = tid - 32; q < hoff[8]; q += T - 32) {
+                int k = 0;
+#pragma unroll
+                for (int j = 1; j < 8; ++j) k += q >= hoff[j];
+                const double2 v = st.halo[halo_offset(k, HE, HC) + (q - hoff[k])];
+                st.x[CAP + q] = v.x;
+                st.y[CAP + q] = v.y;
             }
         }
-        stay_base += total & 0xFFFF;
-        leave_base += total >> 16;
-    }
-    if (flags) atomicOr(&s_flags, flags);
-    __syncthreads();
-    if (tid < 9) {
-        int* ec = reinterpret_cast<int*>(orow + P.L.off_cnt) + (size_t)tc * 16;
-        if (tid < 8) {
-            const int c = s_hout[tid], cap = halo_cap(tid, HE, HC);
-            if (c > cap) atomicOr(&s_flags, kErrHaloOverflow);
-            ec[tid] = min(c, cap);
-        } else {
-            if (leave_base > CO) atomicOr(&s_flags, kErrOutboxOverflow);
-            ec[8] = min(leave_base, CO);
-            P.tcount[lt] = stay_base;
+        consumer_sync<T>();
+        const int n_own = S.n_own, n_apron = S.n_apron;
+
+        // ---- B: bin own + apron particles into the cell table -----------------------------------------
+        for (int q = tid; q < n_own + n_apron; q += T) {
+            const int i = q < n_own ? q : CAP + (q - n_own);
+            const int lrow = axis_cell(st.x[i], P.bincnt) - r0 + 1, lcol = axis_cell(st.y[i], P.bincnt) - c0 + 1;
+            unsigned short cell = 0xFFFFu;
+            if (lrow >= 0 && lrow < W && lcol >= 0 && lcol < W) {
+                cell = (unsigned short)(lrow * W + lcol);
+                const unsigned slot = atomicAdd(&S.cell_cnt[cell], 1u);
+                if (slot < 4u) reinterpret_cast<unsigned short*>(&S.cell_idx[cell])[slot] = (unsigned short)i;
+                else S.overflow = 1;
+            }
+            S.pcell[i] = cell;
         }
+        consumer_sync<T>();
+        const bool overflow = S.overflow != 0;
+
+        // ---- C + D: force over the 3x3 neighbourhood, move; new state stays in registers --------------
+        double nx[PER], ny[PER], nvx[PER], nvy[PER], nax[PER], nay[PER];
+        int nrow[PER], ncol[PER];
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int i = r * T + tid;
+            nrow[r] = ncol[r] = -1;
+            nx[r] = ny[r] = nvx[r] = nvy[r] = nax[r] = nay[r] = 0.0;
+            if (i < n_own) {
+                const double xi = st.x[i], yi = st.y[i];
+                const int cell = S.pcell[i];
+                double ax, ay;
+                int nbc;
+                const int lrow = cell / W, lcol = cell - lrow * W;
+                auto visit = [&](auto&& f) {
+                    if (!overflow) {
+#pragma unroll 1
+                        for (int dr = -1; dr <= 1; ++dr) {
+#pragma unroll
+                            for (int dc = -1; dc <= 1; ++dc) {
+                                const int nc = cell + dr * W + dc;
+                                const unsigned c = S.cell_cnt[nc];
+                                if (c > 0u) {
+                                    unsigned long long w = S.cell_idx[nc];
+                                    const int rk = visit_rank(dr, dc);
+                                    for (unsigned k = 0; k < min(c, 4u); ++k, w >>= 16) {
+                                        const int j = (int)(w & 0xFFFFull);
+                                        f(st.x[j], st.y[j], rk);
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        // a cell of this tile holds more than four particles: exact sweep over everything staged
+#pragma unroll 1
+                        for (int q = 0; q < n_own + n_apron; ++q) {
+                            const int j = q < n_own ? q : CAP + (q - n_own);
+                            const int cj = S.pcell[j];
+                            if (cj == 0xFFFF) continue;
+                            const int dr = cj / W - lrow, dc = cj % W - lcol;
+                            if (dr < -1 || dr > 1 || dc < -1 || dc > 1) continue;
+                            f(st.x[j], st.y[j], visit_rank(dr, dc));
+                        }
+                    }
+                };
+                accumulate_force(xi, yi, visit, ax, ay, nbc);
+                double x = xi, y = yi, vx = st.vx[i], vy = st.vy[i];
+                move_particle(x, y, vx, vy, ax, ay, P.size);
+                nx[r] = x; ny[r] = y; nvx[r] = vx; nvy[r] = vy; nax[r] = ax; nay[r] = ay;
+                nrow[r] = axis_cell(x, P.bincnt);
+                ncol[r] = axis_cell(y, P.bincnt);
+                const int er = nrow[r] - r0, ec = ncol[r] - c0;
+                if (er < 0 || er >= TS || ec < 0 || ec >= TS) {
+                    const int k = atomicAdd(&S.n_leave, 1);
+                    if (k < LMAX) S.leave[k] = i;
+                }
+            }
+        }
+        consumer_sync<T>();
+
+        // ---- E: re-tile ---------------------------------------------------------------------------------
+        const int n_leave_raw = S.n_leave;
+        const int n_leave = min(n_leave_raw, LMAX);
+        const int new_count = n_own - n_leave_raw;
+        if (n_leave > 0) {
+            // holes (leaver slots below new_count) are filled by the stayers at or above new_count, both in
+            // ascending slot order: deterministic regardless of the arrival order in S.leave
+            if (warp == 0) {
+                for (int e = lane; e < n_leave; e += 32) {
+                    const int s = S.leave[e];
+                    if (s < new_count) {
+                        int rank = 0;
+                        for (int f = 0; f < n_leave; ++f) rank += S.leave[f] < s;
+                        S.hole[rank] = s;  // rank among ALL leavers below s == rank among holes (holes are the smallest leaver slots)
+                    }
+                }
+                __syncwarp();
+                for (int m = new_count + lane; m < n_own; m += 32) {
+                    bool is_leaver = false;
+                    int leavers_below = 0;
+                    for (int f = 0; f < n_leave; ++f) {
+                        const int s = S.leave[f];
+                        is_leaver |= s == m;
+                        leavers_below += (s >= new_count && s < m);
+                    }
+                    if (m - new_count < LMAX) S.hole_dst[m - new_count] = is_leaver ? -1 : S.hole[(m - new_count) - leavers_below];
+                }
+            }
+            consumer_sync<T>();
+        }
+
+        char* orow = row_ptr(P.exp_out, P.L, lr);
+        double2* ohxy = reinterpret_cast<double2*>(orow + P.L.off_hxy) + (size_t)tc * D::HL;
+        OutRec* oobox = reinterpret_cast<OutRec*>(orow + P.L.off_obox) + (size_t)tc * CO;
+        int tflags = 0;
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int i = r * T + tid;
+            if (i < n_own) {
+                const int er = nrow[r] - r0, ec = ncol[r] - c0;
+                const bool stay = er >= 0 && er < TS && ec >= 0 && ec < TS;
+                if (stay) {
+                    int d = i;
+                    if (i >= new_count) d = (i - new_count < LMAX) ? S.hole_dst[i - new_count] : -1;
+                    if (d >= 0) {
+                        P.sx[gbase + d] = nx[r];
+                        P.sy[gbase + d] = ny[r];
+                        P.svx[gbase + d] = nvx[r];
+                        P.svy[gbase + d] = nvy[r];
+                        if (kStoreAcc) {
+                            P.sax[gbase + d] = nax[r];
+                            P.say[gbase + d] = nay[r];
+                        }
+                        if (d != i || i >= n_own0) P.sid[gbase + d] = st.id[i];
+                    }
+                    const bool n_ = er == 0, s_ = er == TS - 1, w_ = ec == 0, e_ = ec == TS - 1;
+                    if (n_ | s_ | w_ | e_) {
+                        const double2 q = make_double2(nx[r], ny[r]);
+                        auto put = [&](int list) {
+                            const int idx = atomicAdd(&S.hout[list], 1);
+                            if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
+                        };
+                        if (n_) put(0);
+                        if (s_) put(1);
+                        if (w_) put(2);
+                        if (e_) put(3);
+                        if (n_ && w_) put(4);
+                        if (n_ && e_) put(5);
+                        if (s_ && w_) put(6);
+                        if (s_ && e_) put(7);
+                    }
+                } else {
+                    int rank = 0;
+                    for (int f = 0; f < n_leave; ++f) rank += S.leave[f] < i;
+                    if (rank < CO) {
+                        OutRec rec;
+                        rec.x = nx[r]; rec.y = ny[r]; rec.vx = nvx[r]; rec.vy = nvy[r];
+                        rec.ax = nax[r]; rec.ay = nay[r];
+                        rec.id = st.id[i];
+                        rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+                        oobox[rank] = rec;
+                    }
+                    const int dtr = nrow[r] / TS - tr, dtc = ncol[r] / TS - tc;
+                    if (dtr < -1 || dtr > 1 || dtc < -1 || dtc > 1) tflags |= kErrLostParticle;
+                }
+            }
+        }
+        if (tflags) atomicOr(&S.flags, tflags);
+        fence_proxy_async();  // order this iteration's generic accesses to the stage before the next bulk copies
+        consumer_sync<T>();
+        if (tid == 0) mbar_arrive(&S.empty[it & 1]);  // the producer may refill this stage
+
+        // counts out, reset the per-tile scratch for the next iteration
+        if (tid < 9) {
+            int* ec = reinterpret_cast<int*>(orow + P.L.off_cnt) + (size_t)tc * 16;
+            if (tid < 8) {
+                const int c = S.hout[tid], cap = halo_cap(tid, HE, HC);
+                if (c > cap) atomicOr(&S.flags, kErrHaloOverflow);
+                ec[tid] = min(c, cap);
+                S.hout[tid] = 0;
+                if (tid < 4) atomicMax(&S.hw_halo, c);
+            } else {
+                if (n_leave_raw > CO) atomicOr(&S.flags, kErrOutboxOverflow);
+                ec[8] = min(n_leave_raw, CO);
+                P.tcount[lt] = max(new_count, 0);
+                S.n_leave = 0;
+                S.overflow = 0;
+                S.hw_leave = max(S.hw_leave, n_leave_raw);
+                S.hw_tile = max(S.hw_tile, n_own);
+                S.hw_apron = max(S.hw_apron, n_apron);
+            }
+        }
+        for (int c = tid; c < NC; c += T) S.cell_cnt[c] = 0u;
+        consumer_sync<T>();
     }
-    __syncthreads();
-    if (tid == 0 && s_flags) atomicOr(P.err, s_flags);
+    if (tid == 0) {
+        if (S.flags) atomicOr(P.err, S.flags);
+        atomicMax(P.err + 1, S.hw_leave);
+        atomicMax(P.err + 2, S.hw_halo);
+        atomicMax(P.err + 3, S.hw_tile);
+        atomicMax(P.err + 4, S.hw_apron);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -443,25 +641,21 @@ __global__ void __launch_bounds__(256) tile_fill_kernel(const particle_t* __rest
 
 // first export of halo lists (parity 0) from the freshly filled tiles; outboxes start empty.
 template <int TS>
-__global__ void __launch_bounds__(TileCfg<TS>::THREADS) tile_export_kernel(const TileParams P) {
+__global__ void __launch_bounds__(128) tile_export_kernel(const TileParams P) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    constexpr int T = C::THREADS, CAP = C::CAP, HE = C::HE, HC = C::HC;
+    constexpr int CAP = C::CAP, HE = C::HE, HC = C::HC;
     __shared__ int s_hout[8];
-    __shared__ int s_flags;
     const int tid = threadIdx.x;
-    const int lr = P.lrow0 + blockIdx.x / P.ntx, tc = blockIdx.x % P.ntx;
-    const int tr = P.tr_base + lr;
-    const int lt = lr * P.ntx + tc;
-    const int r0 = tr * TS, c0 = tc * TS;
-    const size_t gbase = (size_t)lt * CAP;
-    const int n = min(P.tcount[lt], CAP);
+    const TileCoord c = tile_coord(P, blockIdx.x);
+    const int r0 = c.tr * TS, c0 = c.tc * TS;
+    const size_t gbase = (size_t)c.lt * CAP;
+    const int n = min(P.tcount[c.lt], CAP);
     if (tid < 8) s_hout[tid] = 0;
-    if (tid == 0) s_flags = 0;
     __syncthreads();
-    char* orow = row_ptr(P.exp_out, P.L, lr);
-    double2* ohxy = reinterpret_cast<double2*>(orow + P.L.off_hxy) + (size_t)tc * D::HL;
-    for (int i = tid; i < n; i += T) {
+    char* orow = row_ptr(P.exp_out, P.L, c.lr);
+    double2* ohxy = reinterpret_cast<double2*>(orow + P.L.off_hxy) + (size_t)c.tc * D::HL;
+    for (int i = tid; i < n; i += blockDim.x) {
         const double x = P.sx[gbase + i], y = P.sy[gbase + i];
         const int er = axis_cell(x, P.bincnt) - r0, ec = axis_cell(y, P.bincnt) - c0;
         const bool n_ = er == 0, s_ = er == TS - 1, w_ = ec == 0, e_ = ec == TS - 1;
@@ -483,11 +677,11 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS) tile_export_kernel(const
     }
     __syncthreads();
     if (tid < 9) {
-        int* ec = reinterpret_cast<int*>(orow + P.L.off_cnt) + (size_t)tc * 16;
+        int* ec = reinterpret_cast<int*>(orow + P.L.off_cnt) + (size_t)c.tc * 16;
         if (tid < 8) {
-            const int c = s_hout[tid], cap = halo_cap(tid, HE, HC);
-            if (c > cap) atomicOr(P.err, kErrHaloOverflow);
-            ec[tid] = min(c, cap);
+            const int k = s_hout[tid], cap = halo_cap(tid, HE, HC);
+            if (k > cap) atomicOr(P.err, kErrHaloOverflow);
+            ec[tid] = min(k, cap);
         } else {
             ec[8] = 0;
         }
@@ -495,16 +689,15 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS) tile_export_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------
-// observation: gather the owned particles (tile stripes + outbox entries that land in owned rows)
+// observation: gather the owned particles (tile stripes + outbox records that land in owned rows)
 // into a compact SoA.  One CTA per tile (ghost rows included: their outboxes may hold particles that
 // have just crossed into this slab).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, int ts, int cap, int co, int lrows_alloc,
-                                                          int tr_begin, int tr_end, bool have_acc, double* __restrict__ gx,
-                                                          double* __restrict__ gy, double* __restrict__ gvx,
-                                                          double* __restrict__ gvy, double* __restrict__ gax,
-                                                          double* __restrict__ gay, int* __restrict__ gid,
-                                                          int* __restrict__ cursor) {
+__global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, int ts, int cap, int co, int tr_begin, int tr_end,
+                                                          bool have_acc, double* __restrict__ gx, double* __restrict__ gy,
+                                                          double* __restrict__ gvx, double* __restrict__ gvy,
+                                                          double* __restrict__ gax, double* __restrict__ gay,
+                                                          int* __restrict__ gid, int* __restrict__ cursor) {
     __shared__ int s_base, s_take[64], s_ntake;
     const int lr = blockIdx.x / P.ntx, tc = blockIdx.x % P.ntx;
     const int tr = P.tr_base + lr;
@@ -514,13 +707,11 @@ __global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, in
     const char* row = row_ptr(P.exp_in, P.L, lr);
     const bool row_valid = tr >= 0 && tr < P.nty;
     const int n_out = row_valid ? min((reinterpret_cast<const int*>(row + P.L.off_cnt) + (size_t)tc * 16)[8], co) : 0;
-    const size_t ob = (size_t)tc * co;
-    const double* ox = reinterpret_cast<const double*>(row + P.L.off_ox) + ob;
-    const double* oy = reinterpret_cast<const double*>(row + P.L.off_oy) + ob;
+    const OutRec* ob = reinterpret_cast<const OutRec*>(row + P.L.off_obox) + (size_t)tc * co;
     if (threadIdx.x == 0) {
         int k = 0;
         for (int e = 0; e < n_out && k < 64; ++e) {
-            const int dtr = axis_cell(ox[e], P.bincnt) / ts;
+            const int dtr = axis_cell(ob[e].x, P.bincnt) / ts;
             if (dtr >= tr_begin && dtr < tr_end) s_take[k++] = e;
         }
         s_ntake = k;
@@ -538,20 +729,16 @@ __global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, in
         gay[base + i] = have_acc ? P.say[gbase + i] : 0.0;
         gid[base + i] = P.sid[gbase + i];
     }
-    const double* ovx = reinterpret_cast<const double*>(row + P.L.off_ovx) + ob;
-    const double* ovy = reinterpret_cast<const double*>(row + P.L.off_ovy) + ob;
-    const double* oax = reinterpret_cast<const double*>(row + P.L.off_oax) + ob;
-    const double* oay = reinterpret_cast<const double*>(row + P.L.off_oay) + ob;
-    const int* oid = reinterpret_cast<const int*>(row + P.L.off_oid) + ob;
     for (int k = threadIdx.x; k < s_ntake; k += blockDim.x) {
-        const int e = s_take[k], d = base + n_tile + k;
-        gx[d] = ox[e];
-        gy[d] = oy[e];
-        gvx[d] = ovx[e];
-        gvy[d] = ovy[e];
-        gax[d] = have_acc ? oax[e] : 0.0;
-        gay[d] = have_acc ? oay[e] : 0.0;
-        gid[d] = oid[e];
+        const OutRec r = ob[s_take[k]];
+        const int d = base + n_tile + k;
+        gx[d] = r.x;
+        gy[d] = r.y;
+        gvx[d] = r.vx;
+        gvy[d] = r.vy;
+        gax[d] = have_acc ? r.ax : 0.0;
+        gay[d] = have_acc ? r.ay : 0.0;
+        gid[d] = r.id;
     }
 }
 
@@ -560,12 +747,13 @@ __global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, in
 // ------------------------------------------------------------------------------------------
 struct TiledEngine {
     DeviceArena mem;
-    int ts = 0, cap = 0, he = 0, hc = 0, co = 0, hl = 0, threads = 0;
+    int ts = 0, cap = 0, he = 0, hc = 0, co = 0, hl = 0, threads = 0, ctas_per_sm = 1;
     size_t smem = 0;
-    int ntx = 0;             // tiles per side
+    int sms = 148;
+    int ntx = 0;                   // tiles per side
     int tr_begin = 0, tr_end = 0;  // owned tile rows (global)
-    int lrows = 0;           // owned rows
-    int lrows_alloc = 0;     // owned + 2 ghost rows
+    int lrows = 0;                 // owned rows
+    int lrows_alloc = 0;           // owned + 2 ghost rows
     ExportLayout L{};
     double *sx = nullptr, *sy = nullptr, *svx = nullptr, *svy = nullptr, *sax = nullptr, *say = nullptr;
     int* sid = nullptr;
@@ -580,9 +768,6 @@ struct TiledEngine {
     SoAView g{};
     int* g_cursor = nullptr;
     int g_capacity = 0;
-    // graph replay of a parity pair
-    cudaGraphExec_t graph2 = nullptr;
-    bool use_graph = false;
 };
 
 static ExportLayout make_layout(int ntx, int hl, int co) {
@@ -595,13 +780,7 @@ static ExportLayout make_layout(int ntx, int hl, int co) {
     };
     L.off_cnt = take((size_t)ntx * 16 * sizeof(int));
     L.off_hxy = take((size_t)ntx * hl * sizeof(double2));
-    L.off_ox = take((size_t)ntx * co * sizeof(double));
-    L.off_oy = take((size_t)ntx * co * sizeof(double));
-    L.off_ovx = take((size_t)ntx * co * sizeof(double));
-    L.off_ovy = take((size_t)ntx * co * sizeof(double));
-    L.off_oax = take((size_t)ntx * co * sizeof(double));
-    L.off_oay = take((size_t)ntx * co * sizeof(double));
-    L.off_oid = take((size_t)ntx * co * sizeof(int));
+    L.off_obox = take((size_t)ntx * co * sizeof(OutRec));
     L.row_bytes = off;
     return L;
 }
@@ -618,6 +797,7 @@ static TileParams make_params(psim_sim* sim, TiledEngine* e, int parity_in) {
     P.nty = e->ntx;
     P.tr_base = e->tr_begin - 1;
     P.lrow0 = 1;
+    P.ntiles = e->lrows * e->ntx;
     P.bincnt = sim->bincnt;
     P.size = sim->size;
     P.err = sim->d_err;
@@ -629,11 +809,12 @@ static int launch_step(psim_sim* sim, TiledEngine* e, int parity_in, bool store_
     if (nrows <= 0) return PSIM_OK;
     TileParams P = make_params(sim, e, parity_in);
     P.lrow0 = lrow0;
-    const int grid = nrows * e->ntx;
+    P.ntiles = nrows * e->ntx;
+    const int grid = std::min(P.ntiles, e->sms * e->ctas_per_sm);
     if (store_acc)
-        tile_step_kernel<TS, true><<<grid, TileCfg<TS>::THREADS, TileDims<TS>::smem_bytes, s>>>(P);
+        tile_step_kernel<TS, true><<<grid, TileCfg<TS>::THREADS + 32, sizeof(TileSmem<TS>), s>>>(P);
     else
-        tile_step_kernel<TS, false><<<grid, TileCfg<TS>::THREADS, TileDims<TS>::smem_bytes, s>>>(P);
+        tile_step_kernel<TS, false><<<grid, TileCfg<TS>::THREADS + 32, sizeof(TileSmem<TS>), s>>>(P);
     ++sim->launches;
     return PSIM_OK;
 }
@@ -654,10 +835,15 @@ static int configure(TiledEngine* e) {
     e->hc = TileCfg<TS>::HC;
     e->co = TileCfg<TS>::CO;
     e->hl = TileDims<TS>::HL;
-    e->threads = TileCfg<TS>::THREADS;
-    e->smem = TileDims<TS>::smem_bytes;
+    e->threads = TileCfg<TS>::THREADS + 32;
+    e->smem = sizeof(TileSmem<TS>);
     PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_step_kernel<TS, false>, TileCfg<TS>::THREADS + 32, e->smem));
+    e->ctas_per_sm = std::max(1, per_sm);
     return PSIM_OK;
 }
 
@@ -676,14 +862,14 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     cudaStream_t s = sim->stream;
     int ts = cfg->tile_cells;
     if (ts == 0) {
-        // enough tiles to fill 148 SMs several times over, else fall to smaller tiles
         const long long cells = (long long)sim->bincnt * sim->bincnt;
-        ts = cells >= 64ll * 64 * 148 * 24 ? 64 : (cells >= 32ll * 32 * 148 * 4 ? 32 : 16);
+        ts = cells >= 32ll * 32 * 148 * 4 ? 32 : 16;
     }
     if (ts != 16 && ts != 32 && ts != 64) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32 or 64 (got %d)", ts);
     auto* e = new TiledEngine();
     sim->tiled = e;
     e->ts = ts;
+    PSIM_CUDA(cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, sim->device));
     if (ts == 16) PSIM_TRY(configure<16>(e));
     if (ts == 32) PSIM_TRY(configure<32>(e));
     if (ts == 64) PSIM_TRY(configure<64>(e));
@@ -753,14 +939,13 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     }
     TileParams P = make_params(sim, e, 1);  // writes exports[0]
     const int grid = e->lrows * e->ntx;
-    if (ts == 16) tile_export_kernel<16><<<grid, TileCfg<16>::THREADS, 0, s>>>(P);
-    if (ts == 32) tile_export_kernel<32><<<grid, TileCfg<32>::THREADS, 0, s>>>(P);
-    if (ts == 64) tile_export_kernel<64><<<grid, TileCfg<64>::THREADS, 0, s>>>(P);
+    if (ts == 16) tile_export_kernel<16><<<grid, 128, 0, s>>>(P);
+    if (ts == 32) tile_export_kernel<32><<<grid, 128, 0, s>>>(P);
+    if (ts == 64) tile_export_kernel<64><<<grid, 128, 0, s>>>(P);
     ++sim->launches;
     PSIM_CUDA(cudaGetLastError());
     e->parity = 0;
     e->acc_valid = true;  // zeros
-    e->use_graph = cfg->use_graph != 0;
     return PSIM_OK;
 }
 
@@ -800,10 +985,14 @@ int tiled_view(psim_sim* sim, SoAView* out) {
         e->g_capacity = sim->n_total;
     }
     PSIM_CUDA(cudaMemsetAsync(e->g_cursor, 0, sizeof(int), s));
+    if (sim->nranks > 1 && !e->ghost_fresh) {
+        PSIM_TRY(tiled_exchange(sim, e->parity, s));
+        e->ghost_fresh = true;
+    }
     TileParams P = make_params(sim, e, e->parity);
-    tile_gather_kernel<<<e->lrows_alloc * e->ntx, 128, 0, s>>>(P, e->ts, e->cap, e->co, e->lrows_alloc, e->tr_begin,
-                                                               e->tr_end, e->acc_valid, e->g.x, e->g.y, e->g.vx, e->g.vy,
-                                                               e->g.ax, e->g.ay, e->g.id, e->g_cursor);
+    tile_gather_kernel<<<e->lrows_alloc * e->ntx, 128, 0, s>>>(P, e->ts, e->cap, e->co, e->tr_begin, e->tr_end, e->acc_valid,
+                                                               e->g.x, e->g.y, e->g.vx, e->g.vy, e->g.ax, e->g.ay, e->g.id,
+                                                               e->g_cursor);
     ++sim->launches;
     PSIM_CUDA(cudaGetLastError());
     int n = 0;
@@ -817,7 +1006,6 @@ int tiled_view(psim_sim* sim, SoAView* out) {
 void tiled_destroy(psim_sim* sim) {
     TiledEngine* e = sim->tiled;
     if (!e) return;
-    if (e->graph2) cudaGraphExecDestroy(e->graph2);
     e->gmem.release();
     e->mem.release();
     delete e;
@@ -831,9 +1019,11 @@ void tiled_info(psim_sim* sim, psim_info_t* out) {
     out->tile_cells = e->ts;
     out->tiles_per_side = e->ntx;
     out->tile_capacity = e->cap;
+    out->outbox_capacity = e->co;
+    out->halo_list_capacity = e->he;
 }
 
-// accessors for psim_comm.cu
+// accessors for psim_comm.cpp
 void tiled_boundary_rows(psim_sim* sim, int parity, char** first_owned, char** last_owned, char** ghost_lo, char** ghost_hi,
                          size_t* row_bytes) {
     TiledEngine* e = sim->tiled;

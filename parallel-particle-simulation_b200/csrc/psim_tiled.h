@@ -6,10 +6,10 @@ namespace psim {
 
 // Byte layout of the exports of ONE tile row (all tiles of the row, section by section), so that a
 // whole boundary row is a single contiguous message.  Per tile: 16 ints of list counts
-// ([0..7] halo lists N S W E NW NE SW SE, [8] outbox), HL double2 halo entries, CO outbox entries
-// as separate x y vx vy ax ay (double) and id (int) streams.
+// ([0..7] halo lists N S W E NW NE SW SE, [8] outbox), HL double2 halo entries, CO outbox records
+// of 64 bytes (x y vx vy ax ay id).
 struct ExportLayout {
-    size_t off_cnt, off_hxy, off_ox, off_oy, off_ovx, off_ovy, off_oax, off_oay, off_oid, row_bytes;
+    size_t off_cnt, off_hxy, off_obox, row_bytes;
 };
 
 }  // namespace psim

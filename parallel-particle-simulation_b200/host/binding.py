@@ -55,7 +55,9 @@ class Info(C.Structure):
     _fields_ = [("engine", C.c_int), ("bin_count", C.c_int), ("tile_cells", C.c_int), ("tiles_per_side", C.c_int),
                 ("tile_capacity", C.c_int), ("device", C.c_int), ("num_parts", C.c_int), ("rank", C.c_int),
                 ("nranks", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("steps_done", C.c_longlong),
-                ("kernel_launches", C.c_longlong), ("device_bytes", C.c_longlong)]
+                ("kernel_launches", C.c_longlong), ("device_bytes", C.c_longlong), ("hw_leavers", C.c_int),
+                ("hw_halo_list", C.c_int), ("hw_tile_population", C.c_int), ("hw_apron", C.c_int),
+                ("outbox_capacity", C.c_int), ("halo_list_capacity", C.c_int)]
 
 
 def lib_path() -> str:
