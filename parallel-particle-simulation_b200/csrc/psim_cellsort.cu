@@ -175,13 +175,14 @@ __global__ void __launch_bounds__(kThreads) force_move_cells_kernel(
         for (int dr = -1; dr <= 1; ++dr) {
             for (int k = k0[dr + 1]; k < k1[dr + 1]; ++k) {
                 const double xj = __ldg(x + k), yj = __ldg(y + k);
-                f(xj, yj, visit_rank(dr, axis_cell(yj, bincnt) - col));
+                f(xj, yj, dr);
             }
         }
     };
+    auto rank_of = [&](double, double yj, int dr) { return visit_rank(dr, axis_cell(yj, bincnt) - col); };
     double ax, ay;
     int nb;
-    accumulate_force(xi, yi, visit, ax, ay, nb);
+    accumulate_force(xi, yi, visit, rank_of, ax, ay, nb);
     double vxi = vx[i], vyi = vy[i];
     move_particle(xi, yi, vxi, vyi, ax, ay, size);
     ox[i] = xi;

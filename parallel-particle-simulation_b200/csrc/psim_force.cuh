@@ -39,9 +39,10 @@ static __device__ __noinline__ void pair_contrib_outlined(double dx, double dy, 
     pair_contrib(dx, dy, r2, *cx, *cy);
 }
 
-// `visit(f)` must call f(xj, yj, rank) once for every candidate neighbour in the particle's 3x3
-// cell neighbourhood (the particle itself may be among them; `rank` is the visit rank of the
-// candidate's cell in the reference's order self,T,B,L,R,TL,TR,BL,BR).
+// `visit(f)` must call f(xj, yj, tag) once for every candidate neighbour in the particle's 3x3
+// cell neighbourhood (the particle itself may be among them); `rank_of(xj, yj, tag)` returns the
+// visit rank of that candidate's cell in the reference's order self,T,B,L,R,TL,TR,BL,BR and is only
+// evaluated on the rare canonical path.
 //
 // Pass 1 only measures distances and remembers the first two in-range neighbours; the expensive
 // coefficient (sqrt + three divisions, reference serial.cpp:29-33) is then evaluated at ONE code
@@ -50,9 +51,9 @@ static __device__ __noinline__ void pair_contrib_outlined(double dx, double dy, 
 // (cell visit rank, x, y) order -- the order the oracle uses (oracle/psim_oracle.c, "Summation
 // order").  Pairs at distance exactly 0 (the self pair the reference evaluates, serial.cpp:107, and
 // coincident particles) contribute coef*0 = -0 and are skipped: a + (-0) == a.
-template <class Visit>
-__device__ __forceinline__ void accumulate_force(double xi, double yi, Visit&& visit, double& ax, double& ay,
-                                                 int& neighbours) {
+template <class Visit, class RankOf>
+__device__ __forceinline__ void accumulate_force(double xi, double yi, Visit&& visit, RankOf&& rank_of, double& ax,
+                                                 double& ay, int& neighbours) {
     int cnt = 0;
     double dx0 = 0.0, dy0 = 0.0, r20 = 0.0, dx1 = 0.0, dy1 = 0.0, r21 = 0.0;
     visit([&](double xj, double yj, int) {
@@ -76,11 +77,11 @@ __device__ __forceinline__ void accumulate_force(double xi, double yi, Visit&& v
             bool found = false;
             int mult = 0;
             double bdx = 0.0, bdy = 0.0, br2 = 0.0;
-            visit([&](double xj, double yj, int rk) {
+            visit([&](double xj, double yj, int tag) {
                 const double dx = __dsub_rn(xj, xi), dy = __dsub_rn(yj, yi);
                 const double r2 = pair_r2(dx, dy);
                 if (r2 > kCutoff2 || r2 == 0.0) return;
-                const NbKey k{rk, xj, yj};
+                const NbKey k{rank_of(xj, yj, tag), xj, yj};
                 if (!key_less(last, k)) return;
                 if (!found || key_less(k, best)) {
                     best = k; found = true; mult = 1; bdx = dx; bdy = dy; br2 = r2;
@@ -101,12 +102,12 @@ __device__ __forceinline__ void accumulate_force(double xi, double yi, Visit&& v
         int rank[kMaxCanonical];
         double dxs[kMaxCanonical], dys[kMaxCanonical], r2s[kMaxCanonical], xs[kMaxCanonical], ys[kMaxCanonical];
         int m = 0;
-        visit([&](double xj, double yj, int rk) {
+        visit([&](double xj, double yj, int tag) {
             const double dx = __dsub_rn(xj, xi), dy = __dsub_rn(yj, yi);
             const double r2 = pair_r2(dx, dy);
             if (r2 > kCutoff2 || r2 == 0.0) return;
             if (m < kMaxCanonical) {
-                rank[m] = rk; dxs[m] = dx; dys[m] = dy; r2s[m] = r2; xs[m] = xj; ys[m] = yj;
+                rank[m] = rank_of(xj, yj, tag); dxs[m] = dx; dys[m] = dy; r2s[m] = r2; xs[m] = xj; ys[m] = yj;
                 ++m;
             }
         });

@@ -52,9 +52,11 @@ namespace psim {
 // THREADS per CTA (each thread owns PER = CAP/THREADS slots), CTAS resident per SM.
 template <int TS> struct TileCfg;
 // THREADS are the CONSUMER threads; every CTA has one more warp, the producer, that only feeds the pipeline.
-template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 64, CS = 4,  THREADS = 128, CTAS = 6; };
-template <> struct TileCfg<32> { static constexpr int CAP = 352,  HE = 32, HC = 8, CO = 64, CS = 8,  THREADS = 352, CTAS = 3; };
-template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 64, CS = 16, THREADS = 576, CTAS = 1; };
+// THREADS is a little above the MEAN population, so nearly every lane has a particle in the first pass;
+// the second pass (PER = 2) only runs for the slots past THREADS.
+template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 64, CS = 4,  THREADS = 64,  CTAS = 8; };
+template <> struct TileCfg<32> { static constexpr int CAP = 352,  HE = 32, HC = 8, CO = 64, CS = 4,  THREADS = 224, CTAS = 3; };
+template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 64, CS = 8,  THREADS = 832, CTAS = 1; };
 
 struct __align__(16) OutRec {  // one migrating particle, 64 bytes
     double x, y, vx, vy, ax, ay;
@@ -69,9 +71,9 @@ template <int TS> struct TileDims {
     static constexpr int HL = 4 * C::HE + 4 * C::HC;      // halo entries a tile exports / stages
     static constexpr int MAXH = HL + 32;                  // apron capacity (halo lists + apron outbox records)
     static constexpr int PTOT = C::CAP + MAXH;
-    static constexpr int PER = C::CAP / C::THREADS;
+    static constexpr int PER = (C::CAP + C::THREADS - 1) / C::THREADS;
     static constexpr int LMAX = C::CO;                    // leaver list capacity
-    static_assert(C::CAP % C::THREADS == 0 && C::CAP % 4 == 0 && PTOT % 2 == 0, "alignment");
+    static_assert(C::CAP % 4 == 0 && PTOT % 2 == 0 && C::THREADS % 32 == 0, "alignment");
 };
 
 // one pipeline stage in shared memory (TMA destinations first, 16-byte aligned)
@@ -89,8 +91,7 @@ template <int TS> struct __align__(16) TileSmem {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
     Stage<TS> st[2];
-    unsigned long long cell_idx[D::NC];       // per cell: up to four particle indices (16 bits each, plain stores)
-    unsigned cell_cnt[D::NC];                 // per cell: population (touched by atomics only)
+    unsigned long long cell[D::NC];           // per cell: population | idx0 | idx1 | idx2 (16 bits each; atomics only)
     unsigned long long full[2];               // mbarriers: stage filled by TMA (producer -> consumers)
     unsigned long long empty[2];              // mbarriers: stage released (consumers -> producer)
     unsigned short pcell[D::PTOT];
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         S.hw_leave = S.hw_halo = S.hw_tile = S.hw_apron = 0;
     }
     if (tid < 8) S.hout[tid] = 0;
-    for (int c = tid; c < NC; c += T + 32) S.cell_cnt[c] = 0u;
+    for (int c = tid; c < NC; c += T + 32) S.cell[c] = 0ull;
     __syncthreads();
 
     // ---- producer warp: runs up to two tiles ahead of the consumers ----------------------------------
@@ -415,8 +416,10 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             unsigned short cell = 0xFFFFu;
             if (lrow >= 0 && lrow < W && lcol >= 0 && lcol < W) {
                 cell = (unsigned short)(lrow * W + lcol);
-                const unsigned slot = atomicAdd(&S.cell_cnt[cell], 1u);
-                if (slot < 4u) reinterpret_cast<unsigned short*>(&S.cell_idx[cell])[slot] = (unsigned short)i;
+                // every modification of the word is atomic, so count and indices never tear
+                unsigned* w32 = reinterpret_cast<unsigned*>(&S.cell[cell]);
+                const unsigned slot = atomicAdd(w32, 1u) & 0xFFFFu;
+                if (slot < 3u) atomicOr(w32 + ((slot + 1u) >> 1), (unsigned)i << (16u * ((slot + 1u) & 1u)));
                 else S.overflow = 1;
             }
             S.pcell[i] = cell;
@@ -425,39 +428,56 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         const bool overflow = S.overflow != 0;
 
         // ---- C + D: force over the 3x3 neighbourhood, move; new state stays in registers --------------
-        double nx[PER], ny[PER], nvx[PER], nvy[PER], nax[PER], nay[PER];
-        int nrow[PER], ncol[PER];
+        // new positions stay in registers (the old ones are still being read by other threads); new velocities
+        // go back to the stage in place (only the owner reads them); accelerations are kept only when stored
+        double nx[PER], ny[PER], nax[kStoreAcc ? PER : 1], nay[kStoreAcc ? PER : 1];
+        int nrc[PER];  // new cell row << 16 | new cell column
 #pragma unroll
         for (int r = 0; r < PER; ++r) {
             const int i = r * T + tid;
-            nrow[r] = ncol[r] = -1;
-            nx[r] = ny[r] = nvx[r] = nvy[r] = nax[r] = nay[r] = 0.0;
+            nrc[r] = 0;
+            nx[r] = ny[r] = 0.0;
             if (i < n_own) {
                 const double xi = st.x[i], yi = st.y[i];
                 const int cell = S.pcell[i];
                 double ax, ay;
                 int nbc;
                 const int lrow = cell / W, lcol = cell - lrow * W;
-                auto visit = [&](auto&& f) {
-                    if (!overflow) {
-#pragma unroll 1
-                        for (int dr = -1; dr <= 1; ++dr) {
+                // pass 0: collect the indices of the (at most eight) other particles in the 3x3 cells into two
+                // registers; the distance loop below then runs over real candidates only, not over cells
+                unsigned long long cand_lo = 0ull, cand_hi = 0ull;
+                int ncand = 0;
+                auto push = [&](unsigned j) {
+                    if (j == (unsigned)i) return;
+                    if (ncand < 4) cand_lo |= (unsigned long long)j << (16 * ncand);
+                    else if (ncand < 8) cand_hi |= (unsigned long long)j << (16 * (ncand - 4));
+                    ++ncand;
+                };
+                if (!overflow) {
 #pragma unroll
-                            for (int dc = -1; dc <= 1; ++dc) {
-                                const int nc = cell + dr * W + dc;
-                                const unsigned c = S.cell_cnt[nc];
-                                if (c > 0u) {
-                                    unsigned long long w = S.cell_idx[nc];
-                                    const int rk = visit_rank(dr, dc);
-                                    for (unsigned k = 0; k < min(c, 4u); ++k, w >>= 16) {
-                                        const int j = (int)(w & 0xFFFFull);
-                                        f(st.x[j], st.y[j], rk);
-                                    }
-                                }
+                    for (int dr = -1; dr <= 1; ++dr) {
+#pragma unroll
+                        for (int dc = -1; dc <= 1; ++dc) {
+                            const unsigned long long w = S.cell[cell + dr * W + dc];
+                            const unsigned c = (unsigned)w & 0xFFFFu;
+                            if (c > 0u) {
+                                push((unsigned)(w >> 16) & 0xFFFFu);
+                                if (c > 1u) push((unsigned)(w >> 32) & 0xFFFFu);
+                                if (c > 2u) push((unsigned)(w >> 48));
                             }
                         }
+                    }
+                }
+                const bool sweep = overflow || ncand > 8;
+                auto visit = [&](auto&& f) {
+                    if (!sweep) {
+#pragma unroll 1
+                        for (int k = 0; k < ncand; ++k) {
+                            const int j = (int)(((k < 4 ? cand_lo : cand_hi) >> (16 * (k & 3))) & 0xFFFFull);
+                            f(st.x[j], st.y[j], j);
+                        }
                     } else {
-                        // a cell of this tile holds more than four particles: exact sweep over everything staged
+                        // a cell near this particle holds more than three particles: exact sweep over everything staged
 #pragma unroll 1
                         for (int q = 0; q < n_own + n_apron; ++q) {
                             const int j = q < n_own ? q : CAP + (q - n_own);
@@ -465,17 +485,24 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                             if (cj == 0xFFFF) continue;
                             const int dr = cj / W - lrow, dc = cj % W - lcol;
                             if (dr < -1 || dr > 1 || dc < -1 || dc > 1) continue;
-                            f(st.x[j], st.y[j], visit_rank(dr, dc));
+                            f(st.x[j], st.y[j], j);
                         }
                     }
                 };
-                accumulate_force(xi, yi, visit, ax, ay, nbc);
+                auto rank_of = [&](double, double, int j) {
+                    const int cj = S.pcell[j];
+                    return visit_rank(cj / W - lrow, cj % W - lcol);
+                };
+                accumulate_force(xi, yi, visit, rank_of, ax, ay, nbc);
                 double x = xi, y = yi, vx = st.vx[i], vy = st.vy[i];
                 move_particle(x, y, vx, vy, ax, ay, P.size);
-                nx[r] = x; ny[r] = y; nvx[r] = vx; nvy[r] = vy; nax[r] = ax; nay[r] = ay;
-                nrow[r] = axis_cell(x, P.bincnt);
-                ncol[r] = axis_cell(y, P.bincnt);
-                const int er = nrow[r] - r0, ec = ncol[r] - c0;
+                nx[r] = x; ny[r] = y;
+                st.vx[i] = vx;
+                st.vy[i] = vy;
+                if (kStoreAcc) { nax[r] = ax; nay[r] = ay; }
+                const int nrow = axis_cell(x, P.bincnt), ncol = axis_cell(y, P.bincnt);
+                nrc[r] = (nrow << 16) | ncol;
+                const int er = nrow - r0, ec = ncol - c0;
                 if (er < 0 || er >= TS || ec < 0 || ec >= TS) {
                     const int k = atomicAdd(&S.n_leave, 1);
                     if (k < LMAX) S.leave[k] = i;
@@ -523,19 +550,21 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         for (int r = 0; r < PER; ++r) {
             const int i = r * T + tid;
             if (i < n_own) {
-                const int er = nrow[r] - r0, ec = ncol[r] - c0;
+                const int nrow = nrc[r] >> 16, ncol = nrc[r] & 0xFFFF;
+                const int er = nrow - r0, ec = ncol - c0;
                 const bool stay = er >= 0 && er < TS && ec >= 0 && ec < TS;
+                const double nvx = st.vx[i], nvy = st.vy[i];
                 if (stay) {
                     int d = i;
                     if (i >= new_count) d = (i - new_count < LMAX) ? S.hole_dst[i - new_count] : -1;
                     if (d >= 0) {
                         P.sx[gbase + d] = nx[r];
                         P.sy[gbase + d] = ny[r];
-                        P.svx[gbase + d] = nvx[r];
-                        P.svy[gbase + d] = nvy[r];
+                        P.svx[gbase + d] = nvx;
+                        P.svy[gbase + d] = nvy;
                         if (kStoreAcc) {
-                            P.sax[gbase + d] = nax[r];
-                            P.say[gbase + d] = nay[r];
+                            P.sax[gbase + d] = nax[kStoreAcc ? r : 0];
+                            P.say[gbase + d] = nay[kStoreAcc ? r : 0];
                         }
                         if (d != i || i >= n_own0) P.sid[gbase + d] = st.id[i];
                     }
@@ -546,27 +575,24 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                             const int idx = atomicAdd(&S.hout[list], 1);
                             if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
                         };
-                        if (n_) put(0);
-                        if (s_) put(1);
-                        if (w_) put(2);
-                        if (e_) put(3);
-                        if (n_ && w_) put(4);
-                        if (n_ && e_) put(5);
-                        if (s_ && w_) put(6);
-                        if (s_ && e_) put(7);
+                        // (with TS >= 3 a cell is on at most one of N/S and one of W/E)
+                        if (n_ | s_) put(n_ ? 0 : 1);
+                        if (w_ | e_) put(w_ ? 2 : 3);
+                        if ((n_ | s_) && (w_ | e_)) put(4 + (s_ ? 2 : 0) + (e_ ? 1 : 0));
                     }
                 } else {
                     int rank = 0;
                     for (int f = 0; f < n_leave; ++f) rank += S.leave[f] < i;
                     if (rank < CO) {
                         OutRec rec;
-                        rec.x = nx[r]; rec.y = ny[r]; rec.vx = nvx[r]; rec.vy = nvy[r];
-                        rec.ax = nax[r]; rec.ay = nay[r];
+                        rec.x = nx[r]; rec.y = ny[r]; rec.vx = nvx; rec.vy = nvy;
+                        rec.ax = kStoreAcc ? nax[kStoreAcc ? r : 0] : 0.0;
+                        rec.ay = kStoreAcc ? nay[kStoreAcc ? r : 0] : 0.0;
                         rec.id = st.id[i];
                         rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
                         oobox[rank] = rec;
                     }
-                    const int dtr = nrow[r] / TS - tr, dtc = ncol[r] / TS - tc;
+                    const int dtr = nrow / TS - tr, dtc = ncol / TS - tc;
                     if (dtr < -1 || dtr > 1 || dtc < -1 || dtc > 1) tflags |= kErrLostParticle;
                 }
             }
@@ -596,7 +622,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 S.hw_apron = max(S.hw_apron, n_apron);
             }
         }
-        for (int c = tid; c < NC; c += T) S.cell_cnt[c] = 0u;
+        for (int c = tid; c < NC; c += T) S.cell[c] = 0ull;
         consumer_sync<T>();
     }
     if (tid == 0) {
