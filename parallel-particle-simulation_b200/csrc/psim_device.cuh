@@ -33,8 +33,21 @@ __device__ __forceinline__ int axis_cell(double v, int bincnt) {
     const double t = __dmul_rn(v, 100.0);
     int c = __double2int_rd(t);
     const double f = __dsub_rn(t, __int2double_rn(c));
-    if (f < 1e-9 || f > 1.0 - 1e-9) c = axis_cell_divide(v);
+    if (fabs(__dsub_rn(f, 0.5)) > 0.5 - 1e-9) c = axis_cell_divide(v);
     return min(max(c, 0), bincnt - 1);
+}
+
+// Both coordinates at once: one rare branch instead of two.
+__device__ __forceinline__ void cell_of(double x, double y, int bincnt, int& row, int& col) {
+    const double tx = __dmul_rn(x, 100.0), ty = __dmul_rn(y, 100.0);
+    int cx = __double2int_rd(tx), cy = __double2int_rd(ty);
+    const double fx = __dsub_rn(tx, __int2double_rn(cx)), fy = __dsub_rn(ty, __int2double_rn(cy));
+    if (fmax(fabs(__dsub_rn(fx, 0.5)), fabs(__dsub_rn(fy, 0.5))) > 0.5 - 1e-9) {
+        cx = axis_cell_divide(x);
+        cy = axis_cell_divide(y);
+    }
+    row = min(max(cx, 0), bincnt - 1);
+    col = min(max(cy, 0), bincnt - 1);
 }
 
 // Rank of a neighbour cell (dr, dc) in the reference's visiting order
@@ -66,14 +79,16 @@ __device__ __forceinline__ void move_particle(double& x, double& y, double& vx, 
     vy = __dadd_rn(vy, __dmul_rn(ay, kDt));
     x = __dadd_rn(x, __dmul_rn(vx, kDt));
     y = __dadd_rn(y, __dmul_rn(vy, kDt));
-    const double two_size = __dmul_rn(2.0, size);
-    while (x < 0 || x > size) {
-        x = x < 0 ? -x : __dsub_rn(two_size, x);
-        vx = -vx;
-    }
-    while (y < 0 || y > size) {
-        y = y < 0 ? -y : __dsub_rn(two_size, y);
-        vy = -vy;
+    if (x < 0 || x > size || y < 0 || y > size) {   // one rare branch on the common path
+        const double two_size = __dmul_rn(2.0, size);
+        while (x < 0 || x > size) {
+            x = x < 0 ? -x : __dsub_rn(two_size, x);
+            vx = -vx;
+        }
+        while (y < 0 || y > size) {
+            y = y < 0 ? -y : __dsub_rn(two_size, y);
+            vy = -vy;
+        }
     }
 }
 

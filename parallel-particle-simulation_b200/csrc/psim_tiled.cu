@@ -1,33 +1,35 @@
 // psim_tiled.cu -- the "tiled" engine: persistent tile-resident particles, one fused kernel per step.
 //
 // Layout in HBM.  The box is cut into square tiles of TS x TS cutoff cells.  Every tile owns a stripe
-// of CAP particle slots in five structure-of-arrays streams (x, y, vx, vy, id; plus ax, ay written
-// only on steps whose accelerations are kept).  A tile's live particles occupy slots [0, count) and a
-// particle keeps its slot for as long as it stays in the tile.  Steady-state HBM traffic is therefore
-// read 32 B + write 32 B per particle-step plus a few percent of boundary lists: there is no global
-// histogram, scan or scatter in the time loop.
+// of CAP particle slots in three vectorised streams -- pos (double2 x,y), vel (double2 vx,vy), id (int)
+// -- plus acc (double2 ax,ay), written only on steps whose accelerations are kept.  A tile's live
+// particles occupy slots [0, count).  The stripes and the tile "exports" (eight halo lists with the
+// positions of the particles in the tile's boundary cells, and an outbox with the full records of the
+// particles that left the tile) are double buffered by step parity: a step reads parity p and writes
+// p^1, so no CTA ever reads what another CTA of the same launch writes.  Steady-state HBM traffic is
+// read 36 B + write 36 B per particle-step plus a few percent of exports: there is no global histogram,
+// scan or scatter in the time loop.
 //
 // Per step one persistent kernel (tile_step_kernel); a CTA walks tiles blockIdx.x, +gridDim.x, ...
-// with a two-stage shared-memory pipeline fed by TMA bulk copies (cp.async.bulk + mbarrier):
-//   while tile k is computed, the bulk copies of tile k+1 (its 5 stripes, the 8 neighbour halo lists
-//   and the 9 surrounding outboxes) are in flight and the list counts of tile k+2 are being fetched,
-//   so no warp ever waits on a dependent chain of global loads.
-// Compute on a staged tile:
-//   A. ingest: particles that entered the tile last step (outbox records of the 3x3 tiles) are
-//      appended; the one-cell apron is assembled from the neighbours' edge / corner halo lists (and
-//      from outbox records that sit in the apron)
-//   B. bin own + apron particles into a (TS+2)^2 table IN SHARED MEMORY: per cutoff cell a
-//      population word and up to four particle indices (one atomicAdd + one 16-bit store per particle;
-//      reference part3/gpu.cu:92-112 does this in global memory with 16 slots per cell)
-//   C. force: every own particle reads the 9 words of its 3x3 neighbourhood (reference
-//      part1/serial.cpp:102-117, 19-36), canonical summation order; cells with more than four
-//      particles switch the tile to an exact all-pairs sweep
-//   D. move + reflect (reference part1/serial.cpp:46-61) in registers
-//   E. re-tile: stayers are written back to their own slot, leavers go to the tile's outbox and the
-//      holes they leave are filled from the tail; particles in the tile's boundary cells are
-//      appended to the edge / corner halo lists the neighbours read next step.
-// Halo lists and outboxes ("exports") are double buffered by step parity: a step reads parity p and
-// writes parity p^1, so no CTA ever reads what another CTA of the same launch writes.
+// A producer warp runs two tiles ahead and feeds a two-stage shared-memory pipeline with TMA bulk
+// copies (cp.async.bulk + mbarrier): the tile's three stripes, the eight neighbour halo lists (landing
+// directly behind the own particles as the "apron") and the nine surrounding outboxes.  The consumer
+// warps then do, with four CTA barriers per tile:
+//   A. ingest + bin: particles that entered the tile last step (outbox records of the 3x3 tiles) are
+//      appended; own and apron particles are binned into a (TS+2)^2 cell table IN SHARED MEMORY --
+//      per cell the head of a linked list (one atomicExch per particle; reference part3/gpu.cu:92-112
+//      does this in global memory with 16 fixed slots per cell) and one bit in a per-row occupancy map
+//   B. search: every own particle takes the 9 occupancy bits of its 3x3 neighbourhood (reference
+//      part1/serial.cpp:102-117), walks only the non-empty cells and tests candidates in FP32 on
+//      tile-relative coordinates against a slightly widened cutoff; survivors go to a CTA-wide pair list
+//   C. pair evaluation, dense: one lane per listed pair redoes the distance test in exact FP64 and, if in
+//      range, evaluates the coefficient (sqrt + three divisions, reference part1/serial.cpp:19-36).  The
+//      expensive FP64 sequence runs once per tile with full lanes instead of once per warp with ~3.
+//   D. sum (<= 2 contributions are order independent; more take the canonical-order path), move + reflect
+//      (reference part1/serial.cpp:46-61), new cell, stay / leave decision, warp ballots
+//   E. re-tile: stayers are written to the other stripe buffer compacted by a ballot prefix, leavers go to
+//      the tile's outbox, particles in the tile's boundary cells are appended to the edge / corner halo
+//      lists the neighbours read next step.
 //
 // Slabs (precedent reference part2/mpi.cpp:258-270,296-365): a rank owns a
 // contiguous range of tile rows plus one ghost tile row on each side that holds only exports.  The
@@ -49,67 +51,76 @@ namespace psim {
 // CO outbox records per tile of which the first CS are staged in shared memory by the pipeline (a
 // tile that receives more from one neighbour reads the rest straight from global memory: this only
 // happens in bursts, e.g. a column of the initial lattice that sits exactly on a tile boundary),
-// THREADS per CTA (each thread owns PER = CAP/THREADS slots), CTAS resident per SM.
+// NP pair-list entries, THREADS consumer threads per CTA (every CTA has one more warp, the producer),
+// CTAS resident per SM.  THREADS is a little above the MEAN population, so nearly every lane has a
+// particle in the first pass; the second pass (PER = 2) only runs for the slots past THREADS.
 template <int TS> struct TileCfg;
-// THREADS are the CONSUMER threads; every CTA has one more warp, the producer, that only feeds the pipeline.
-// THREADS is a little above the MEAN population, so nearly every lane has a particle in the first pass;
-// the second pass (PER = 2) only runs for the slots past THREADS.
-template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 64, CS = 4,  THREADS = 64,  CTAS = 8; };
-template <> struct TileCfg<32> { static constexpr int CAP = 352,  HE = 32, HC = 8, CO = 64, CS = 4,  THREADS = 224, CTAS = 3; };
-template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 64, CS = 8,  THREADS = 832, CTAS = 1; };
+template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 64, CS = 3, NP = 32,  THREADS = 64,  CTAS = 8; };
+template <> struct TileCfg<32> { static constexpr int CAP = 352,  HE = 32, HC = 8, CO = 64, CS = 4, NP = 96,  THREADS = 224, CTAS = 4; };
+template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 64, CS = 6, NP = 320, THREADS = 832, CTAS = 1; };
 
 struct __align__(16) OutRec {  // one migrating particle, 64 bytes
     double x, y, vx, vy, ax, ay;
     int id;
-    int pad[3];
+    int row, col;  // its cell (row = floor(x/0.01), col = floor(y/0.01)), computed once by the sender
+    int pad;
 };
 static_assert(sizeof(OutRec) == 64, "OutRec must be 64 bytes");
+
+constexpr unsigned kEmpty = 0xFFFFu;          // end of a cell's list / empty cell
+constexpr float kPrefilter2 = 1.001e-4f;      // FP32 candidate test: cutoff^2 widened by 1e-3 (float error is < 1e-5)
 
 template <int TS> struct TileDims {
     using C = TileCfg<TS>;
     static constexpr int W = TS + 2, NC = W * W;
+    static constexpr int RW = (W + 31) / 32 + 1;          // occupancy words per cell row (+1: funnel shifts read one past)
     static constexpr int HL = 4 * C::HE + 4 * C::HC;      // halo entries a tile exports / stages
     static constexpr int MAXH = HL + 32;                  // apron capacity (halo lists + apron outbox records)
     static constexpr int PTOT = C::CAP + MAXH;
     static constexpr int PER = (C::CAP + C::THREADS - 1) / C::THREADS;
-    static constexpr int LMAX = C::CO;                    // leaver list capacity
-    static_assert(C::CAP % 4 == 0 && PTOT % 2 == 0 && C::THREADS % 32 == 0, "alignment");
+    static constexpr int NW = C::THREADS / 32;            // consumer warps
+    static constexpr int OS = 9 * C::CS;                  // staged outbox records
+    static_assert(C::CAP % 4 == 0 && C::THREADS % 32 == 0 && NW <= 32 && PTOT < 0xFFFF, "configuration");
 };
 
-// one pipeline stage in shared memory (TMA destinations first, 16-byte aligned)
+// one pipeline stage in shared memory (TMA destinations, 16-byte aligned)
 template <int TS> struct __align__(16) Stage {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    double x[D::PTOT], y[D::PTOT];   // own [0, n) then apron [CAP, CAP + n_apron)
-    double vx[C::CAP], vy[C::CAP];
+    double2 xy[D::PTOT];    // own [0, n) then apron [CAP, CAP + n_apron)
+    double2 v[C::CAP];
     int id[C::CAP];
-    double2 halo[D::HL];             // raw halo lists of the 8 neighbours
-    OutRec obox[9][C::CS];           // first CS records of the outboxes of the 3x3 tiles
+    OutRec obox[D::OS];     // staged records of the outboxes of the 3x3 tiles, contiguous
 };
 
 template <int TS> struct __align__(16) TileSmem {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
     Stage<TS> st[2];
-    unsigned long long cell[D::NC];           // per cell: population | idx0 | idx1 | idx2 (16 bits each; atomics only)
+    double2 pres[C::NP];                      // pair list: contribution of pair t to its first particle
+    float2 rel[D::PTOT];                      // tile-relative FP32 positions (prefilter only)
+    unsigned head[2][D::NC];                  // per cell: first particle of its list (kEmpty: none); double buffered by tile
+    unsigned rowbits[2][D::W * D::RW];        // per cell row: occupancy bit per cell
+    unsigned pij[C::NP];                      // pair list: i | j << 16
     unsigned long long full[2];               // mbarriers: stage filled by TMA (producer -> consumers)
     unsigned long long empty[2];              // mbarriers: stage released (consumers -> producer)
-    unsigned short pcell[D::PTOT];
-    int cnts[2][20];                          // list counts of the staged tiles: [0] own, [1..8] halo, [9..17] outbox
-    int leave[D::LMAX];                       // slots of the particles that leave this step
-    int hole_dst[D::LMAX];                    // destination slot of the tail stayers that fill holes
-    int hole[D::LMAX];
-    int n_own, n_apron, n_leave, flags, overflow;
-    int hw_leave, hw_halo, hw_tile, hw_apron;   // high-water marks over the tiles this CTA processed
+    unsigned short next[D::PTOT];             // next particle in the same cell
+    unsigned short pcell[2][D::PTOT];         // cell of a binned particle (0xFFFF: not binned); double buffered like head
+    int cnts[2][20];                          // staged tiles: [0] own, [1..8] halo lists, [9..17] outboxes, [18] halo total, [19] staged outbox records
     int hout[8];
+    int n_own, n_apron, npairs, flags;
+    int n_stay, n_leave;                      // stayers / leavers of the current tile (warp-aggregated atomics)
+    int hw_leave, hw_halo, hw_tile, hw_apron;   // high-water marks over the tiles this CTA processed
 };
 
 __host__ __device__ inline int halo_offset(int list, int HE, int HC) { return list < 4 ? list * HE : 4 * HE + (list - 4) * HC; }
 __host__ __device__ inline int halo_cap(int list, int HE, int HC) { return list < 4 ? HE : HC; }
 
 struct TileParams {
-    double *sx, *sy, *svx, *svy, *sax, *say;
-    int* sid;
+    const double2 *pos_in, *vel_in;
+    const int* id_in;
+    double2 *pos_out, *vel_out, *acc_out;
+    int* id_out;
     int* tcount;
     const char* exp_in;
     char* exp_out;
@@ -149,17 +160,38 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// consumers: the data is normally there already, spin tightly
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// producer: waits for a whole tile of consumer work; let the hardware suspend the warp (time hint in ns)
+// so that the wait does not steal issue slots from the consumers
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+            : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -189,11 +221,37 @@ __device__ __forceinline__ TileCoord tile_coord(const TileParams& P, int t) {
     return c;
 }
 
+// walks the tiles first, first + G, first + 2G, ... of a launch without a division per tile
+struct TileWalker {
+    int lr, tc, gq, gr;
+    __device__ __forceinline__ void init(const TileParams& P, int first, int G) {
+        lr = P.lrow0 + first / P.ntx;
+        tc = first % P.ntx;
+        gq = G / P.ntx;
+        gr = G % P.ntx;
+    }
+    __device__ __forceinline__ void advance(const TileParams& P) {
+        tc += gr;
+        lr += gq;
+        if (tc >= P.ntx) {
+            tc -= P.ntx;
+            ++lr;
+        }
+    }
+    __device__ __forceinline__ TileCoord coord(const TileParams& P) const {
+        TileCoord c;
+        c.lr = lr;
+        c.tc = tc;
+        c.tr = P.tr_base + lr;
+        c.lt = lr * P.ntx + tc;
+        return c;
+    }
+};
+
 // list count j of tile t: j = 0 own population, 1..8 apron sources, 9..17 outboxes of the 3x3 tiles
 template <int TS>
-__device__ __forceinline__ int load_count(const TileParams& P, int t, int j) {
+__device__ __forceinline__ int load_count(const TileParams& P, const TileCoord& c, int j) {
     using C = TileCfg<TS>;
-    const TileCoord c = tile_coord(P, t);
     if (j == 0) return min(P.tcount[c.lt], C::CAP);
     int dr, dc, list;
     if (j <= 8) {
@@ -209,54 +267,97 @@ __device__ __forceinline__ int load_count(const TileParams& P, int t, int j) {
     return min(ec[list], list == 8 ? C::CO : halo_cap(list, C::HE, C::HC));
 }
 
-// Issue the bulk copies of tile t into `st` (one warp; lane j owns copy j).
-//   lanes 0-3: x y vx vy stripes, lane 4: id stripe, lanes 5-12: apron sources, lanes 13-21: outboxes
+// Producer: fetch the list counts of tile t, publish them in `cnt`, issue the bulk copies into `st`.
+//   copy 0 pos, 1 vel, 2 id, 3..10 apron source k = copy-3 (straight to its final place behind the own
+//   particles), 11..19 outbox nb = copy-11 (first CS records, packed back to back)
 template <int TS>
-__device__ __forceinline__ void issue_tile_loads(const TileParams& P, int t, Stage<TS>& st, const int* cnt,
-                                                 unsigned long long* bar, int lane) {
+__device__ __forceinline__ void produce_tile(const TileParams& P, const TileCoord c, Stage<TS>& st, int* cnt, unsigned long long* bar,
+                                             unsigned long long* empty_bar, bool wait_empty, unsigned empty_parity, int lane) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    const TileCoord c = tile_coord(P, t);
+    const int cj = lane < 18 ? load_count<TS>(P, c, lane) : 0;
+    // exclusive prefixes: halo entries over lanes 1..8, staged outbox records over lanes 9..17
+    const int hv = (lane >= 1 && lane <= 8) ? cj : 0;
+    const int ov = (lane >= 9 && lane <= 17) ? min(cj, C::CS) : 0;
+    int hs = hv, os = ov;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, hs, o), b = __shfl_up_sync(0xffffffffu, os, o);
+        if (lane >= o) {
+            hs += a;
+            os += b;
+        }
+    }
+    const int n_halo = __shfl_sync(0xffffffffu, hs, 8), n_staged = __shfl_sync(0xffffffffu, os, 17);
+    const int n = __shfl_sync(0xffffffffu, cj, 0);
+    // what this lane copies
+    const int src_lane = lane < 3 ? 0 : lane < 11 ? lane - 2 : lane < 20 ? lane - 2 : 0;   // lane holding the count of my copy
+    const int my_cnt = __shfl_sync(0xffffffffu, cj, src_lane);
+    const int my_hoff = __shfl_sync(0xffffffffu, hs - hv, src_lane);
+    const int my_ooff = __shfl_sync(0xffffffffu, os - ov, src_lane);
+    if (wait_empty) mbar_wait_relaxed(empty_bar, empty_parity);   // the tile two iterations back has left the stage
+    if (lane < 18) cnt[lane] = cj;
+    if (lane == 18) cnt[18] = n_halo;
+    if (lane == 19) cnt[19] = n_staged;
     const size_t gbase = (size_t)c.lt * C::CAP;
     const void* src = nullptr;
     void* dst = nullptr;
     unsigned bytes = 0;
-    if (lane < 5) {
-        const int n = cnt[0];
-        if (lane < 4) {
-            bytes = (unsigned)((n + 1) >> 1) * 16u;
-            src = (lane == 0 ? P.sx : lane == 1 ? P.sy : lane == 2 ? P.svx : P.svy) + gbase;
-            dst = lane == 0 ? st.x : lane == 1 ? st.y : lane == 2 ? st.vx : st.vy;
-        } else {
-            bytes = (unsigned)((n + 3) >> 2) * 16u;
-            src = P.sid + gbase;
-            dst = st.id;
-        }
-    } else if (lane < 13) {
-        const int k = lane - 5;
+    if (lane == 0) {
+        bytes = (unsigned)n * 16u; src = P.pos_in + gbase; dst = st.xy;
+    } else if (lane == 1) {
+        bytes = (unsigned)n * 16u; src = P.vel_in + gbase; dst = st.v;
+    } else if (lane == 2) {
+        bytes = (unsigned)((n + 3) >> 2) * 16u; src = P.id_in + gbase; dst = st.id;
+    } else if (lane < 11) {
         int dr, dc, list;
-        halo_source(k, dr, dc, list);
-        bytes = (unsigned)cnt[1 + k] * 16u;
+        halo_source(lane - 3, dr, dc, list);
+        bytes = (unsigned)my_cnt * 16u;
         if (bytes) {
             src = reinterpret_cast<const double2*>(row_ptr(P.exp_in, P.L, c.lr + dr) + P.L.off_hxy) +
                   (size_t)(c.tc + dc) * D::HL + halo_offset(list, C::HE, C::HC);
-            dst = st.halo + halo_offset(k, C::HE, C::HC);
+            dst = st.xy + C::CAP + my_hoff;
         }
-    } else if (lane < 22) {
-        const int nb = lane - 13;
+    } else if (lane < 20) {
+        const int nb = lane - 11;
         const int dr = nb / 3 - 1, dc = nb % 3 - 1;
-        bytes = (unsigned)min(cnt[9 + nb], C::CS) * (unsigned)sizeof(OutRec);
+        bytes = (unsigned)min(my_cnt, C::CS) * (unsigned)sizeof(OutRec);
         if (bytes) {
             src = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, c.lr + dr) + P.L.off_obox) + (size_t)(c.tc + dc) * C::CO;
-            dst = st.obox[nb];
+            dst = st.obox + my_ooff;
         }
     }
     unsigned total = bytes;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    __syncwarp();   // counts are in shared memory before the barrier can complete
     if (lane == 0) mbar_arrive_expect_tx(bar, total);
     __syncwarp();
     if (bytes) tma_load_1d(dst, src, bytes, bar);
+}
+
+// Rare path: exact FP64 walk of the 3x3 neighbourhood with canonical-order summation (particles whose
+// prefilter found three or more candidates, or whose pairs did not fit the pair list).
+template <int W>
+static __device__ __noinline__ double2 slow_force(const double2* xy, const unsigned* head, const unsigned short* next, int i,
+                                                  int cell) {
+    const double2 pi = xy[i];
+    auto visit = [&](auto&& f) {
+#pragma unroll 1
+        for (int k = 0; k < 9; ++k) {
+            unsigned h = head[cell + (k / 3 - 1) * W + (k % 3 - 1)];
+            while (h != kEmpty) {
+                const double2 pj = xy[h];
+                f(pj.x, pj.y, k);
+                h = next[h];
+            }
+        }
+    };
+    auto rank_of = [&](double, double, int k) { return visit_rank(k / 3 - 1, k % 3 - 1); };
+    double ax, ay;
+    int nb;
+    accumulate_force(pi.x, pi.y, visit, rank_of, ax, ay, nb);
+    return make_double2(ax, ay);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -266,8 +367,8 @@ template <int TS, bool kStoreAcc>
 __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) tile_step_kernel(const TileParams P) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, NC = D::NC, PER = D::PER;
-    constexpr int HE = C::HE, HC = C::HC, CO = C::CO, LMAX = D::LMAX;
+    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, NC = D::NC, PER = D::PER, RW = D::RW, NW = D::NW;
+    constexpr int HE = C::HE, HC = C::HC, CO = C::CO, NP = C::NP;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem<TS>& S = *reinterpret_cast<TileSmem<TS>*>(smem_raw);
@@ -281,111 +382,127 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
     if (tid == 0) {
         mbar_init(&S.full[0], 1);
         mbar_init(&S.full[1], 1);
-        mbar_init(&S.empty[0], 1);
-        mbar_init(&S.empty[1], 1);
+        mbar_init(&S.empty[0], NW);
+        mbar_init(&S.empty[1], NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        S.n_leave = 0;
+        S.npairs = 0;
         S.flags = 0;
-        S.overflow = 0;
+        S.n_stay = S.n_leave = 0;
         S.hw_leave = S.hw_halo = S.hw_tile = S.hw_apron = 0;
     }
     if (tid < 8) S.hout[tid] = 0;
-    for (int c = tid; c < NC; c += T + 32) S.cell[c] = 0ull;
+    for (int c = tid; c < 2 * NC; c += T + 32) (&S.head[0][0])[c] = kEmpty;
+    for (int c = tid; c < 2 * W * RW; c += T + 32) (&S.rowbits[0][0])[c] = 0u;
     __syncthreads();
 
     // ---- producer warp: runs up to two tiles ahead of the consumers ----------------------------------
-    if (warp == T / 32) {
+    TileWalker walk;
+    walk.init(P, first, G);
+    if (warp == NW) {
         for (int j = 0;; ++j) {
             const int t = first + j * G;
             if (t >= P.ntiles) break;
-            const int c = lane < 18 ? load_count<TS>(P, t, lane) : 0;
-            if (j >= 2) mbar_wait(&S.empty[j & 1], (unsigned)(((j >> 1) - 1) & 1));  // tile j-2 has left the stage
-            if (lane < 18) S.cnts[j & 1][lane] = c;
-            __syncwarp();
-            issue_tile_loads<TS>(P, t, S.st[j & 1], S.cnts[j & 1], &S.full[j & 1], lane);
+            produce_tile<TS>(P, walk.coord(P), S.st[j & 1], S.cnts[j & 1], &S.full[j & 1], &S.empty[j & 1], j >= 2,
+                             (unsigned)(((j >> 1) - 1) & 1), lane);
+            walk.advance(P);
         }
         return;
     }
 
     // ---- consumers ----------------------------------------------------------------------------------
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int prev_lr = -1, prev_tc = 0;   // tile whose halo-list counts still have to be published
+    auto publish_halo_counts = [&](int done_lr, int done_tc) {
+        // tid < 8: list `tid` of that tile is complete (all appends happened before the last barrier)
+        int* ec = reinterpret_cast<int*>(row_ptr(P.exp_out, P.L, done_lr) + P.L.off_cnt) + (size_t)done_tc * 16;
+        const int k = S.hout[tid], cap = halo_cap(tid, HE, HC);
+        if (k > cap) atomicOr(&S.flags, kErrHaloOverflow);
+        ec[tid] = min(k, cap);
+        S.hout[tid] = 0;
+        if (tid < 4) atomicMax(&S.hw_halo, k);
+    };
+
     for (int it = 0;; ++it) {
         const int t = first + it * G;
         if (t >= P.ntiles) break;
-        Stage<TS>& st = S.st[it & 1];
-        const int* cnt = S.cnts[it & 1];
-        const TileCoord tc_ = tile_coord(P, t);
+        const int sb = it & 1;   // stage and cell-table buffer of this tile
+        Stage<TS>& st = S.st[sb];
+        const int* cnt = S.cnts[sb];
+        unsigned* head = S.head[sb];
+        unsigned* rowbits = S.rowbits[sb];
+        unsigned short* pcell = S.pcell[sb];
+        const TileCoord tc_ = walk.coord(P);
         const int tr = tc_.tr, tc = tc_.tc, lt = tc_.lt, lr = tc_.lr;
         const int r0 = tr * TS, c0 = tc * TS;
         const size_t gbase = (size_t)lt * CAP;
+        const double ox = (double)(r0 - 1) * kBin, oy = (double)(c0 - 1) * kBin;   // origin of the tile-relative FP32 frame
 
-        mbar_wait(&S.full[it & 1], (unsigned)((it >> 1) & 1));  // this tile's bytes (and counts) have landed
+        mbar_wait(&S.full[sb], (unsigned)((it >> 1) & 1));  // this tile's bytes (and counts) have landed
 
-        const int n_own0 = cnt[0];
+        const int n_own0 = cnt[0], n_halo = cnt[18];
 
-        // ---- A: ingest newcomers and assemble the apron ---------------------------------------------
-        int hoff[9];
-        hoff[0] = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) hoff[k + 1] = hoff[k] + cnt[1 + k];
+        // bin particle p (index into st.xy) that lies in local cell (lrow, lcol) of the (TS+2)^2 table
+        auto bin = [&](int p, int lrow, int lcol, double x, double y) {
+            const int cell = lrow * W + lcol;
+            const unsigned old = atomicExch(&head[cell], (unsigned)p);
+            S.next[p] = (unsigned short)old;
+            pcell[p] = (unsigned short)cell;
+            atomicOr(&rowbits[lrow * RW + (lcol >> 5)], 1u << (lcol & 31));
+            S.rel[p] = make_float2(__double2float_rn(__dsub_rn(x, ox)), __double2float_rn(__dsub_rn(y, oy)));
+        };
+
+        // ---- A: ingest newcomers, bin own + apron particles ---------------------------------------------
         if (warp == 0) {
             // outbox records of the 3x3 tiles: records now in my tile are appended to my stripe, records in my
-            // apron ring become apron particles (after the halo-list entries).  One lane per staged record.
-            const unsigned lt_mask = (1u << lane) - 1u;
-            int n_own = n_own0, n_ap = hoff[8], flags = 0;
+            // apron ring become apron particles (after the halo-list entries).  One lane per record.
+            int n_own = n_own0, n_ap = n_halo, flags = 0;
             auto take = [&](bool valid, const OutRec* rec) {
                 bool mine = false, apron = false;
-                double x = 0, y = 0;
+                int lrow = 0, lcol = 0;
                 if (valid) {
-                    x = rec->x;
-                    y = rec->y;
-                    const int row_c = axis_cell(x, P.bincnt), col_c = axis_cell(y, P.bincnt);
-                    mine = row_c / TS == tr && col_c / TS == tc;
-                    apron = !mine && row_c >= r0 - 1 && row_c <= r0 + TS && col_c >= c0 - 1 && col_c <= c0 + TS;
+                    lrow = rec->row - (r0 - 1);
+                    lcol = rec->col - (c0 - 1);
+                    const bool ring = lrow >= 0 && lrow <= TS + 1 && lcol >= 0 && lcol <= TS + 1;
+                    mine = lrow >= 1 && lrow <= TS && lcol >= 1 && lcol <= TS;
+                    apron = ring && !mine;
                 }
                 const unsigned mm = __ballot_sync(0xffffffffu, mine), am = __ballot_sync(0xffffffffu, apron);
                 if (mine) {
                     const int d = n_own + __popc(mm & lt_mask);
                     if (d < CAP) {
-                        st.x[d] = x;
-                        st.y[d] = y;
-                        st.vx[d] = rec->vx;
-                        st.vy[d] = rec->vy;
+                        const double x = rec->x, y = rec->y;
+                        st.xy[d] = make_double2(x, y);
+                        st.v[d] = make_double2(rec->vx, rec->vy);
                         st.id[d] = rec->id;
+                        bin(d, lrow, lcol, x, y);
                     }
                 }
                 if (apron) {
                     const int hh = n_ap + __popc(am & lt_mask);
                     if (hh < D::MAXH) {
-                        st.x[CAP + hh] = x;
-                        st.y[CAP + hh] = y;
+                        const double x = rec->x, y = rec->y;
+                        st.xy[CAP + hh] = make_double2(x, y);
+                        bin(CAP + hh, lrow, lcol, x, y);
                     }
                 }
                 n_own += __popc(mm);
                 n_ap += __popc(am);
             };
-            int total_out = 0, beyond = 0;
+            const int n_staged = cnt[19];
+#pragma unroll 1
+            for (int q0 = 0; q0 < n_staged; q0 += 32) take(q0 + lane < n_staged, &st.obox[min(q0 + lane, D::OS - 1)]);
+            int beyond = 0;
 #pragma unroll
-            for (int nb = 0; nb < 9; ++nb) {
-                total_out += cnt[9 + nb];
-                beyond |= cnt[9 + nb] > C::CS;
-            }
-            if (total_out > 0) {
+            for (int nb = 0; nb < 9; ++nb) beyond |= cnt[9 + nb] > C::CS;
+            if (beyond) {
+                // bursts only: records past the staged CS are read from the neighbour's outbox in global memory
 #pragma unroll 1
-                for (int q0 = 0; q0 < 9 * C::CS; q0 += 32) {
-                    const int q = q0 + lane, nb = q / C::CS, e = q % C::CS;
-                    const bool valid = q < 9 * C::CS && e < cnt[9 + min(nb, 8)];
-                    take(valid, &st.obox[min(nb, 8)][e]);
-                }
-                if (beyond) {
-                    // bursts only: records past the staged CS are read from the neighbour's outbox in global memory
-#pragma unroll 1
-                    for (int nb = 0; nb < 9; ++nb) {
-                        const int c = cnt[9 + nb];
-                        if (c <= C::CS) continue;
-                        const OutRec* grec = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, lr + nb / 3 - 1) + P.L.off_obox) +
-                                             (size_t)(tc + nb % 3 - 1) * CO;
-                        for (int e0 = C::CS; e0 < c; e0 += 32) take(e0 + lane < c, grec + e0 + lane);
-                    }
+                for (int nb = 0; nb < 9; ++nb) {
+                    const int c = cnt[9 + nb];
+                    if (c <= C::CS) continue;
+                    const OutRec* grec = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, lr + nb / 3 - 1) + P.L.off_obox) +
+                                         (size_t)(tc + nb % 3 - 1) * CO;
+                    for (int e0 = C::CS; e0 < c; e0 += 32) take(e0 + lane < c, grec + min(e0 + lane, c - 1));
                 }
             }
             if (n_own > CAP) { flags |= kErrTileOverflow; n_own = CAP; }
@@ -395,153 +512,147 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 S.n_apron = n_ap;
                 if (flags) atomicOr(&S.flags, flags);
             }
-        } else {
-            // halo lists -> contiguous apron positions
-            for (int q = tid - 32; q < hoff[8]; q += T - 32) {
-                int k = 0;
-#pragma unroll
-                for (int j = 1; j < 8; ++j) k += q >= hoff[j];
-                const double2 v = st.halo[halo_offset(k, HE, HC) + (q - hoff[k])];
-                st.x[CAP + q] = v.x;
-                st.y[CAP + q] = v.y;
-            }
         }
-        consumer_sync<T>();
+        // own particles that were already here and the halo-list apron
+        for (int q = tid; q < n_own0 + n_halo; q += T) {
+            const int p = q < n_own0 ? q : CAP + (q - n_own0);
+            const double2 a = st.xy[p];
+            int lrow, lcol;
+            cell_of(a.x, a.y, P.bincnt, lrow, lcol);
+            lrow -= r0 - 1;
+            lcol -= c0 - 1;
+            if (lrow >= 0 && lrow < W && lcol >= 0 && lcol < W) bin(p, lrow, lcol, a.x, a.y);
+            else pcell[p] = 0xFFFFu;
+        }
+        consumer_sync<T>();   // (1) cell table complete
+        if (prev_lr >= 0 && tid < 8) publish_halo_counts(prev_lr, prev_tc);
         const int n_own = S.n_own, n_apron = S.n_apron;
 
-        // ---- B: bin own + apron particles into the cell table -----------------------------------------
-        for (int q = tid; q < n_own + n_apron; q += T) {
-            const int i = q < n_own ? q : CAP + (q - n_own);
-            const int lrow = axis_cell(st.x[i], P.bincnt) - r0 + 1, lcol = axis_cell(st.y[i], P.bincnt) - c0 + 1;
-            unsigned short cell = 0xFFFFu;
-            if (lrow >= 0 && lrow < W && lcol >= 0 && lcol < W) {
-                cell = (unsigned short)(lrow * W + lcol);
-                // every modification of the word is atomic, so count and indices never tear
-                unsigned* w32 = reinterpret_cast<unsigned*>(&S.cell[cell]);
-                const unsigned slot = atomicAdd(w32, 1u) & 0xFFFFu;
-                if (slot < 3u) atomicOr(w32 + ((slot + 1u) >> 1), (unsigned)i << (16u * ((slot + 1u) & 1u)));
-                else S.overflow = 1;
+        // ---- B: candidate search in FP32 ------------------------------------------------------------------
+        int pb[PER];   // fc (0, 1, 2; 3 = exact path) | pair-list base << 2
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int i = r * T + tid;
+            pb[r] = 0;
+            if (i < n_own) {
+                const int cell = pcell[i];
+                const int lrow = cell / W, lcol = cell - lrow * W;
+                const float2 ri = S.rel[i];
+                // 9 occupancy bits of the 3x3 neighbourhood, bit 3*(dr+1) + (dc+1)
+                const unsigned* rb = rowbits + (lrow - 1) * RW + ((lcol - 1) >> 5);
+                const unsigned sh = (unsigned)(lcol - 1) & 31u;
+                unsigned m = 0;
+#pragma unroll
+                for (int dr = 0; dr < 3; ++dr) m |= (__funnelshift_r(rb[dr * RW], rb[dr * RW + 1], sh) & 7u) << (3 * dr);
+                if (head[cell] == (unsigned)i && S.next[i] == kEmpty) m &= ~16u;   // alone in my own cell
+                int fc = 0;
+                unsigned cand = 0;   // the last two prefilter hits, 16 bits each
+                while (m) {
+                    const int k = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const int q = (k * 11) >> 5;   // k / 3
+                    unsigned h = head[cell + q * (W - 3) + k - (W + 1)];
+                    do {   // the occupancy bit guarantees a non-empty list
+                        const float2 rj = S.rel[h];
+                        const unsigned hn = S.next[h];
+                        const float dx = rj.x - ri.x, dy = rj.y - ri.y;
+                        const float r2 = dx * dx + dy * dy;
+                        if (r2 <= kPrefilter2 && h != (unsigned)i) {
+                            cand = (cand << 16) | h;
+                            ++fc;
+                        }
+                        h = hn;
+                    } while (h != kEmpty);
+                }
+                if (fc >= 3) {
+                    pb[r] = 3;
+                } else if (fc > 0) {
+                    const int base = atomicAdd(&S.npairs, fc);
+                    if (base + fc <= NP) {
+                        S.pij[base] = (unsigned)i | (cand << 16);
+                        if (fc == 2) S.pij[base + 1] = (unsigned)i | (cand & 0xFFFF0000u);
+                        pb[r] = fc | (base << 2);
+                    } else {
+                        pb[r] = 3;
+                    }
+                }
             }
-            S.pcell[i] = cell;
         }
-        consumer_sync<T>();
-        const bool overflow = S.overflow != 0;
+        consumer_sync<T>();   // (2) pair list complete
 
-        // ---- C + D: force over the 3x3 neighbourhood, move; new state stays in registers --------------
-        // new positions stay in registers (the old ones are still being read by other threads); new velocities
-        // go back to the stage in place (only the owner reads them); accelerations are kept only when stored
+        // ---- C: exact pair evaluation, one lane per pair (the last warps first: they have the fewest particles) ----
+        {
+            const int np = min(S.npairs, NP);
+            for (int u = T - 1 - tid; u < np; u += T) {
+                const unsigned ij = S.pij[u];
+                const double2 a = st.xy[ij & 0xFFFFu], b = st.xy[ij >> 16];
+                const double dx = __dsub_rn(b.x, a.x), dy = __dsub_rn(b.y, a.y);
+                const double r2 = pair_r2(dx, dy);
+                double cx = 0.0, cy = 0.0;
+                if (!(r2 > kCutoff2) && r2 != 0.0) pair_contrib(dx, dy, r2, cx, cy);
+                S.pres[u] = make_double2(cx, cy);   // (+0, +0) for a prefilter false positive: neutral in the sum
+            }
+        }
+        consumer_sync<T>();   // (3) contributions ready
+
+        // ---- D: sum, move, new cell, stay / leave ----------------------------------------------------------------
         double nx[PER], ny[PER], nax[kStoreAcc ? PER : 1], nay[kStoreAcc ? PER : 1];
         int nrc[PER];  // new cell row << 16 | new cell column
+        int dst[PER];  // stayer: slot in the output stripe; leaver: -1 - outbox rank
 #pragma unroll
         for (int r = 0; r < PER; ++r) {
             const int i = r * T + tid;
             nrc[r] = 0;
+            dst[r] = 0;
             nx[r] = ny[r] = 0.0;
+            bool stay = false, leave = false;
             if (i < n_own) {
-                const double xi = st.x[i], yi = st.y[i];
-                const int cell = S.pcell[i];
-                double ax, ay;
-                int nbc;
-                const int lrow = cell / W, lcol = cell - lrow * W;
-                // pass 0: collect the indices of the (at most eight) other particles in the 3x3 cells into two
-                // registers; the distance loop below then runs over real candidates only, not over cells
-                unsigned long long cand_lo = 0ull, cand_hi = 0ull;
-                int ncand = 0;
-                auto push = [&](unsigned j) {
-                    if (j == (unsigned)i) return;
-                    if (ncand < 4) cand_lo |= (unsigned long long)j << (16 * ncand);
-                    else if (ncand < 8) cand_hi |= (unsigned long long)j << (16 * (ncand - 4));
-                    ++ncand;
-                };
-                if (!overflow) {
-#pragma unroll
-                    for (int dr = -1; dr <= 1; ++dr) {
-#pragma unroll
-                        for (int dc = -1; dc <= 1; ++dc) {
-                            const unsigned long long w = S.cell[cell + dr * W + dc];
-                            const unsigned c = (unsigned)w & 0xFFFFu;
-                            if (c > 0u) {
-                                push((unsigned)(w >> 16) & 0xFFFFu);
-                                if (c > 1u) push((unsigned)(w >> 32) & 0xFFFFu);
-                                if (c > 2u) push((unsigned)(w >> 48));
-                            }
-                        }
+                double ax = 0.0, ay = 0.0;
+                const int code = pb[r], fc = code & 3;
+                if (fc == 3) {
+                    const double2 a = slow_force<W>(st.xy, head, S.next, i, pcell[i]);
+                    ax = a.x;
+                    ay = a.y;
+                } else if (fc > 0) {
+                    const double2 c0_ = S.pres[code >> 2];
+                    ax = __dadd_rn(ax, c0_.x);
+                    ay = __dadd_rn(ay, c0_.y);
+                    if (fc == 2) {
+                        const double2 c1_ = S.pres[(code >> 2) + 1];
+                        ax = __dadd_rn(ax, c1_.x);
+                        ay = __dadd_rn(ay, c1_.y);
                     }
                 }
-                const bool sweep = overflow || ncand > 8;
-                auto visit = [&](auto&& f) {
-                    if (!sweep) {
-#pragma unroll 1
-                        for (int k = 0; k < ncand; ++k) {
-                            const int j = (int)(((k < 4 ? cand_lo : cand_hi) >> (16 * (k & 3))) & 0xFFFFull);
-                            f(st.x[j], st.y[j], j);
-                        }
-                    } else {
-                        // a cell near this particle holds more than three particles: exact sweep over everything staged
-#pragma unroll 1
-                        for (int q = 0; q < n_own + n_apron; ++q) {
-                            const int j = q < n_own ? q : CAP + (q - n_own);
-                            const int cj = S.pcell[j];
-                            if (cj == 0xFFFF) continue;
-                            const int dr = cj / W - lrow, dc = cj % W - lcol;
-                            if (dr < -1 || dr > 1 || dc < -1 || dc > 1) continue;
-                            f(st.x[j], st.y[j], j);
-                        }
-                    }
-                };
-                auto rank_of = [&](double, double, int j) {
-                    const int cj = S.pcell[j];
-                    return visit_rank(cj / W - lrow, cj % W - lcol);
-                };
-                accumulate_force(xi, yi, visit, rank_of, ax, ay, nbc);
-                double x = xi, y = yi, vx = st.vx[i], vy = st.vy[i];
-                move_particle(x, y, vx, vy, ax, ay, P.size);
+                const double2 p = st.xy[i];
+                double2 v = st.v[i];
+                double x = p.x, y = p.y;
+                move_particle(x, y, v.x, v.y, ax, ay, P.size);
                 nx[r] = x; ny[r] = y;
-                st.vx[i] = vx;
-                st.vy[i] = vy;
+                st.v[i] = v;   // only the owner reads it again
                 if (kStoreAcc) { nax[r] = ax; nay[r] = ay; }
-                const int nrow = axis_cell(x, P.bincnt), ncol = axis_cell(y, P.bincnt);
+                int nrow, ncol;
+                cell_of(x, y, P.bincnt, nrow, ncol);
                 nrc[r] = (nrow << 16) | ncol;
-                const int er = nrow - r0, ec = ncol - c0;
-                if (er < 0 || er >= TS || ec < 0 || ec >= TS) {
-                    const int k = atomicAdd(&S.n_leave, 1);
-                    if (k < LMAX) S.leave[k] = i;
+                const unsigned er = (unsigned)(nrow - r0), ec = (unsigned)(ncol - c0);
+                stay = er < (unsigned)TS && ec < (unsigned)TS;
+                leave = !stay;
+            }
+            if (r * T < n_own) {   // warp-uniform: this pass has particles
+                // destination slots: one atomic per warp, lanes take consecutive slots after the warp's base
+                const unsigned sm = __ballot_sync(0xffffffffu, stay), lm = __ballot_sync(0xffffffffu, leave);
+                int sbase = 0, lbase = 0;
+                if (lane == 0) {
+                    if (sm) sbase = atomicAdd(&S.n_stay, __popc(sm));
+                    if (lm) lbase = atomicAdd(&S.n_leave, __popc(lm));
                 }
+                sbase = __shfl_sync(0xffffffffu, sbase, 0);
+                lbase = __shfl_sync(0xffffffffu, lbase, 0);
+                dst[r] = stay ? sbase + __popc(sm & lt_mask) : leave ? -1 - (lbase + __popc(lm & lt_mask)) : 0;
             }
         }
-        consumer_sync<T>();
+        consumer_sync<T>();   // (4) warp counts published; nobody reads the cell table or the positions any more
 
         // ---- E: re-tile ---------------------------------------------------------------------------------
-        const int n_leave_raw = S.n_leave;
-        const int n_leave = min(n_leave_raw, LMAX);
-        const int new_count = n_own - n_leave_raw;
-        if (n_leave > 0) {
-            // holes (leaver slots below new_count) are filled by the stayers at or above new_count, both in
-            // ascending slot order: deterministic regardless of the arrival order in S.leave
-            if (warp == 0) {
-                for (int e = lane; e < n_leave; e += 32) {
-                    const int s = S.leave[e];
-                    if (s < new_count) {
-                        int rank = 0;
-                        for (int f = 0; f < n_leave; ++f) rank += S.leave[f] < s;
-                        S.hole[rank] = s;  // rank among ALL leavers below s == rank among holes (holes are the smallest leaver slots)
-                    }
-                }
-                __syncwarp();
-                for (int m = new_count + lane; m < n_own; m += 32) {
-                    bool is_leaver = false;
-                    int leavers_below = 0;
-                    for (int f = 0; f < n_leave; ++f) {
-                        const int s = S.leave[f];
-                        is_leaver |= s == m;
-                        leavers_below += (s >= new_count && s < m);
-                    }
-                    if (m - new_count < LMAX) S.hole_dst[m - new_count] = is_leaver ? -1 : S.hole[(m - new_count) - leavers_below];
-                }
-            }
-            consumer_sync<T>();
-        }
-
         char* orow = row_ptr(P.exp_out, P.L, lr);
         double2* ohxy = reinterpret_cast<double2*>(orow + P.L.off_hxy) + (size_t)tc * D::HL;
         OutRec* oobox = reinterpret_cast<OutRec*>(orow + P.L.off_obox) + (size_t)tc * CO;
@@ -552,44 +663,40 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             if (i < n_own) {
                 const int nrow = nrc[r] >> 16, ncol = nrc[r] & 0xFFFF;
                 const int er = nrow - r0, ec = ncol - c0;
-                const bool stay = er >= 0 && er < TS && ec >= 0 && ec < TS;
-                const double nvx = st.vx[i], nvy = st.vy[i];
-                if (stay) {
-                    int d = i;
-                    if (i >= new_count) d = (i - new_count < LMAX) ? S.hole_dst[i - new_count] : -1;
-                    if (d >= 0) {
-                        P.sx[gbase + d] = nx[r];
-                        P.sy[gbase + d] = ny[r];
-                        P.svx[gbase + d] = nvx;
-                        P.svy[gbase + d] = nvy;
-                        if (kStoreAcc) {
-                            P.sax[gbase + d] = nax[kStoreAcc ? r : 0];
-                            P.say[gbase + d] = nay[kStoreAcc ? r : 0];
-                        }
-                        if (d != i || i >= n_own0) P.sid[gbase + d] = st.id[i];
-                    }
+                const double2 nv = st.v[i];
+                const double2 q = make_double2(nx[r], ny[r]);
+                head[pcell[i]] = kEmpty;   // leave the cell table clean for the tile after next
+                if (dst[r] >= 0) {
+                    const size_t d = gbase + (size_t)dst[r];
+                    P.pos_out[d] = q;
+                    P.vel_out[d] = nv;
+                    P.id_out[d] = st.id[i];
+                    if (kStoreAcc) P.acc_out[d] = make_double2(nax[kStoreAcc ? r : 0], nay[kStoreAcc ? r : 0]);
+                    // boundary cells: append to the edge list(s) and, in a corner cell, the corner list
+                    // (with TS >= 3 a cell is on at most one of N/S and one of W/E)
                     const bool n_ = er == 0, s_ = er == TS - 1, w_ = ec == 0, e_ = ec == TS - 1;
                     if (n_ | s_ | w_ | e_) {
-                        const double2 q = make_double2(nx[r], ny[r]);
-                        auto put = [&](int list) {
+                        unsigned lists = 0;   // up to three list ids, 4 bits each
+                        int nl = 0;
+                        if (n_ | s_) { lists = s_ ? 1u : 0u; nl = 1; }
+                        if (w_ | e_) { lists |= (e_ ? 3u : 2u) << (4 * nl); ++nl; }
+                        if (nl == 2) { lists |= (4u + (s_ ? 2u : 0u) + (e_ ? 1u : 0u)) << 8; nl = 3; }
+#pragma unroll 1
+                        for (int k = 0; k < nl; ++k) {
+                            const int list = (int)((lists >> (4 * k)) & 15u);
                             const int idx = atomicAdd(&S.hout[list], 1);
                             if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
-                        };
-                        // (with TS >= 3 a cell is on at most one of N/S and one of W/E)
-                        if (n_ | s_) put(n_ ? 0 : 1);
-                        if (w_ | e_) put(w_ ? 2 : 3);
-                        if ((n_ | s_) && (w_ | e_)) put(4 + (s_ ? 2 : 0) + (e_ ? 1 : 0));
+                        }
                     }
                 } else {
-                    int rank = 0;
-                    for (int f = 0; f < n_leave; ++f) rank += S.leave[f] < i;
+                    const int rank = -1 - dst[r];
                     if (rank < CO) {
                         OutRec rec;
-                        rec.x = nx[r]; rec.y = ny[r]; rec.vx = nvx; rec.vy = nvy;
+                        rec.x = q.x; rec.y = q.y; rec.vx = nv.x; rec.vy = nv.y;
                         rec.ax = kStoreAcc ? nax[kStoreAcc ? r : 0] : 0.0;
                         rec.ay = kStoreAcc ? nay[kStoreAcc ? r : 0] : 0.0;
                         rec.id = st.id[i];
-                        rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+                        rec.row = nrow; rec.col = ncol; rec.pad = 0;
                         oobox[rank] = rec;
                     }
                     const int dtr = nrow / TS - tr, dtc = ncol / TS - tc;
@@ -597,34 +704,35 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 }
             }
         }
-        if (tflags) atomicOr(&S.flags, tflags);
-        fence_proxy_async();  // order this iteration's generic accesses to the stage before the next bulk copies
-        consumer_sync<T>();
-        if (tid == 0) mbar_arrive(&S.empty[it & 1]);  // the producer may refill this stage
-
-        // counts out, reset the per-tile scratch for the next iteration
-        if (tid < 9) {
-            int* ec = reinterpret_cast<int*>(orow + P.L.off_cnt) + (size_t)tc * 16;
-            if (tid < 8) {
-                const int c = S.hout[tid], cap = halo_cap(tid, HE, HC);
-                if (c > cap) atomicOr(&S.flags, kErrHaloOverflow);
-                ec[tid] = min(c, cap);
-                S.hout[tid] = 0;
-                if (tid < 4) atomicMax(&S.hw_halo, c);
-            } else {
-                if (n_leave_raw > CO) atomicOr(&S.flags, kErrOutboxOverflow);
-                ec[8] = min(n_leave_raw, CO);
-                P.tcount[lt] = max(new_count, 0);
-                S.n_leave = 0;
-                S.overflow = 0;
-                S.hw_leave = max(S.hw_leave, n_leave_raw);
-                S.hw_tile = max(S.hw_tile, n_own);
-                S.hw_apron = max(S.hw_apron, n_apron);
-            }
+        // apron particles leave the cell table too; the occupancy map is small enough to clear whole
+        for (int q = tid; q < n_apron; q += T) {
+            const unsigned c = pcell[CAP + q];
+            if (c != 0xFFFFu) head[c] = kEmpty;
         }
-        for (int c = tid; c < NC; c += T) S.cell[c] = 0ull;
-        consumer_sync<T>();
+        for (int c = tid; c < W * RW; c += T) rowbits[c] = 0u;
+        if (tflags) atomicOr(&S.flags, tflags);
+        if (tid == 0) {
+            const int stay_base = S.n_stay, leave_base = S.n_leave;   // tile totals
+            S.n_stay = S.n_leave = 0;
+            int* ecnt = reinterpret_cast<int*>(orow + P.L.off_cnt) + (size_t)tc * 16;
+            if (leave_base > CO) atomicOr(&S.flags, kErrOutboxOverflow);
+            ecnt[8] = min(leave_base, CO);
+            P.tcount[lt] = stay_base;
+            S.npairs = 0;
+            S.hw_leave = max(S.hw_leave, leave_base);
+            S.hw_tile = max(S.hw_tile, n_own);
+            S.hw_apron = max(S.hw_apron, n_apron);
+        }
+        fence_proxy_async();  // order this iteration's generic accesses to the stage before the next bulk copies
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.empty[sb]);  // the producer may refill this stage once every consumer warp has arrived
+        prev_lr = lr;
+        prev_tc = tc;
+        walk.advance(P);
     }
+    consumer_sync<T>();   // all halo-list appends of the last tile are done
+    if (prev_lr >= 0 && tid < 8) publish_halo_counts(prev_lr, prev_tc);
+    consumer_sync<T>();
     if (tid == 0) {
         if (S.flags) atomicOr(P.err, S.flags);
         atomicMax(P.err + 1, S.hw_leave);
@@ -641,8 +749,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
 // harmless because forces are summed in a canonical order.
 __global__ void __launch_bounds__(256) tile_fill_kernel(const particle_t* __restrict__ p, int n, int id0, int bincnt,
                                                         int ts, int cap, int ntx, int tr_begin, int tr_end,
-                                                        int tr_base, double* __restrict__ sx, double* __restrict__ sy,
-                                                        double* __restrict__ svx, double* __restrict__ svy,
+                                                        int tr_base, double2* __restrict__ pos, double2* __restrict__ vel,
                                                         int* __restrict__ sid, int* __restrict__ tcount,
                                                         int* __restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -658,10 +765,8 @@ __global__ void __launch_bounds__(256) tile_fill_kernel(const particle_t* __rest
         return;
     }
     const size_t d = (size_t)lt * cap + slot;
-    sx[d] = a.x;
-    sy[d] = a.y;
-    svx[d] = b.x;
-    svy[d] = b.y;
+    pos[d] = a;
+    vel[d] = b;
     sid[d] = id0 + i;
 }
 
@@ -682,11 +787,10 @@ __global__ void __launch_bounds__(128) tile_export_kernel(const TileParams P) {
     char* orow = row_ptr(P.exp_out, P.L, c.lr);
     double2* ohxy = reinterpret_cast<double2*>(orow + P.L.off_hxy) + (size_t)c.tc * D::HL;
     for (int i = tid; i < n; i += blockDim.x) {
-        const double x = P.sx[gbase + i], y = P.sy[gbase + i];
-        const int er = axis_cell(x, P.bincnt) - r0, ec = axis_cell(y, P.bincnt) - c0;
+        const double2 q = P.pos_in[gbase + i];
+        const int er = axis_cell(q.x, P.bincnt) - r0, ec = axis_cell(q.y, P.bincnt) - c0;
         const bool n_ = er == 0, s_ = er == TS - 1, w_ = ec == 0, e_ = ec == TS - 1;
         if (n_ | s_ | w_ | e_) {
-            const double2 q = make_double2(x, y);
             auto put = [&](int list) {
                 const int idx = atomicAdd(&s_hout[list], 1);
                 if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
@@ -719,8 +823,9 @@ __global__ void __launch_bounds__(128) tile_export_kernel(const TileParams P) {
 // into a compact SoA.  One CTA per tile (ghost rows included: their outboxes may hold particles that
 // have just crossed into this slab).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, int ts, int cap, int co, int tr_begin, int tr_end,
-                                                          bool have_acc, double* __restrict__ gx, double* __restrict__ gy,
+__global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, const double2* __restrict__ acc, int ts, int cap,
+                                                          int co, int tr_begin, int tr_end, bool have_acc,
+                                                          double* __restrict__ gx, double* __restrict__ gy,
                                                           double* __restrict__ gvx, double* __restrict__ gvy,
                                                           double* __restrict__ gax, double* __restrict__ gay,
                                                           int* __restrict__ gid, int* __restrict__ cursor) {
@@ -737,7 +842,7 @@ __global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, in
     if (threadIdx.x == 0) {
         int k = 0;
         for (int e = 0; e < n_out && k < 64; ++e) {
-            const int dtr = axis_cell(ob[e].x, P.bincnt) / ts;
+            const int dtr = ob[e].row / ts;
             if (dtr >= tr_begin && dtr < tr_end) s_take[k++] = e;
         }
         s_ntake = k;
@@ -747,13 +852,15 @@ __global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, in
     const int base = s_base;
     const size_t gbase = (size_t)lt * cap;
     for (int i = threadIdx.x; i < n_tile; i += blockDim.x) {
-        gx[base + i] = P.sx[gbase + i];
-        gy[base + i] = P.sy[gbase + i];
-        gvx[base + i] = P.svx[gbase + i];
-        gvy[base + i] = P.svy[gbase + i];
-        gax[base + i] = have_acc ? P.sax[gbase + i] : 0.0;
-        gay[base + i] = have_acc ? P.say[gbase + i] : 0.0;
-        gid[base + i] = P.sid[gbase + i];
+        const double2 p = P.pos_in[gbase + i], v = P.vel_in[gbase + i];
+        const double2 a = have_acc ? acc[gbase + i] : make_double2(0.0, 0.0);
+        gx[base + i] = p.x;
+        gy[base + i] = p.y;
+        gvx[base + i] = v.x;
+        gvy[base + i] = v.y;
+        gax[base + i] = a.x;
+        gay[base + i] = a.y;
+        gid[base + i] = P.id_in[gbase + i];
     }
     for (int k = threadIdx.x; k < s_ntake; k += blockDim.x) {
         const OutRec r = ob[s_take[k]];
@@ -781,13 +888,14 @@ struct TiledEngine {
     int lrows = 0;                 // owned rows
     int lrows_alloc = 0;           // owned + 2 ghost rows
     ExportLayout L{};
-    double *sx = nullptr, *sy = nullptr, *svx = nullptr, *svy = nullptr, *sax = nullptr, *say = nullptr;
-    int* sid = nullptr;
+    // stripes and exports, double buffered by step parity: buffer [parity] is what the next step reads
+    double2 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr}, *acc = nullptr;
+    int* sid[2] = {nullptr, nullptr};
     int* tcount = nullptr;
     char* exports[2] = {nullptr, nullptr};
     size_t export_bytes = 0;  // one parity
-    int parity = 0;           // exports[parity] is what the next step reads
-    bool acc_valid = false;
+    int parity = 0;
+    bool acc_valid = false;    // acc holds the accelerations of the step that produced buffer [parity]
     bool ghost_fresh = false;  // ghost rows hold the neighbours' exports of the current parity
     // gather scratch
     DeviceArena gmem;
@@ -813,8 +921,9 @@ static ExportLayout make_layout(int ntx, int hl, int co) {
 
 static TileParams make_params(psim_sim* sim, TiledEngine* e, int parity_in) {
     TileParams P{};
-    P.sx = e->sx; P.sy = e->sy; P.svx = e->svx; P.svy = e->svy; P.sax = e->sax; P.say = e->say;
-    P.sid = e->sid;
+    P.pos_in = e->pos[parity_in]; P.vel_in = e->vel[parity_in]; P.id_in = e->sid[parity_in];
+    P.pos_out = e->pos[parity_in ^ 1]; P.vel_out = e->vel[parity_in ^ 1]; P.id_out = e->sid[parity_in ^ 1];
+    P.acc_out = e->acc;
     P.tcount = e->tcount;
     P.exp_in = e->exports[parity_in];
     P.exp_out = e->exports[parity_in ^ 1];
@@ -910,21 +1019,17 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     e->export_bytes = e->L.row_bytes * (size_t)e->lrows_alloc;
 
     const size_t slots = (size_t)e->lrows_alloc * e->ntx * e->cap;
-    PSIM_TRY(e->mem.alloc(&e->sx, slots));
-    PSIM_TRY(e->mem.alloc(&e->sy, slots));
-    PSIM_TRY(e->mem.alloc(&e->svx, slots));
-    PSIM_TRY(e->mem.alloc(&e->svy, slots));
-    PSIM_TRY(e->mem.alloc(&e->sax, slots));
-    PSIM_TRY(e->mem.alloc(&e->say, slots));
-    PSIM_TRY(e->mem.alloc(&e->sid, slots));
+    for (int b = 0; b < 2; ++b) {
+        PSIM_TRY(e->mem.alloc(&e->pos[b], slots));
+        PSIM_TRY(e->mem.alloc(&e->vel[b], slots));
+        PSIM_TRY(e->mem.alloc(&e->sid[b], slots));
+        PSIM_TRY(e->mem.alloc(&e->exports[b], e->export_bytes));
+        PSIM_CUDA(cudaMemsetAsync(e->exports[b], 0, e->export_bytes, s));
+    }
+    PSIM_TRY(e->mem.alloc(&e->acc, slots));
     PSIM_TRY(e->mem.alloc(&e->tcount, (size_t)e->lrows_alloc * e->ntx));
-    PSIM_TRY(e->mem.alloc(&e->exports[0], e->export_bytes));
-    PSIM_TRY(e->mem.alloc(&e->exports[1], e->export_bytes));
     PSIM_CUDA(cudaMemsetAsync(e->tcount, 0, sizeof(int) * (size_t)e->lrows_alloc * e->ntx, s));
-    PSIM_CUDA(cudaMemsetAsync(e->exports[0], 0, e->export_bytes, s));
-    PSIM_CUDA(cudaMemsetAsync(e->exports[1], 0, e->export_bytes, s));
-    PSIM_CUDA(cudaMemsetAsync(e->sax, 0, sizeof(double) * slots, s));
-    PSIM_CUDA(cudaMemsetAsync(e->say, 0, sizeof(double) * slots, s));
+    PSIM_CUDA(cudaMemsetAsync(e->acc, 0, sizeof(double2) * slots, s));
     // fill: device input is read in place; host input is streamed through a bounded staging buffer
     // (a slab keeps only its own rows, so no rank ever holds the whole array on the device)
     {
@@ -940,8 +1045,8 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
                 src = d_stage;
             }
             tile_fill_kernel<<<(m + 255) / 256, 256, 0, s>>>(src, m, off, sim->bincnt, ts, e->cap, e->ntx, e->tr_begin,
-                                                             e->tr_end, e->tr_begin - 1, e->sx, e->sy, e->svx, e->svy,
-                                                             e->sid, e->tcount, sim->d_err);
+                                                             e->tr_end, e->tr_begin - 1, e->pos[0], e->vel[0], e->sid[0],
+                                                             e->tcount, sim->d_err);
             ++sim->launches;
             if (!parts_on_device) PSIM_CUDA(cudaStreamSynchronize(s));
         }
@@ -963,7 +1068,8 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
                         worst, e->cap);
         }
     }
-    TileParams P = make_params(sim, e, 1);  // writes exports[0]
+    TileParams P = make_params(sim, e, 0);   // reads stripes [0] ...
+    P.exp_out = e->exports[0];               // ... and writes the exports of the same parity
     const int grid = e->lrows * e->ntx;
     if (ts == 16) tile_export_kernel<16><<<grid, 128, 0, s>>>(P);
     if (ts == 32) tile_export_kernel<32><<<grid, 128, 0, s>>>(P);
@@ -1016,9 +1122,9 @@ int tiled_view(psim_sim* sim, SoAView* out) {
         e->ghost_fresh = true;
     }
     TileParams P = make_params(sim, e, e->parity);
-    tile_gather_kernel<<<e->lrows_alloc * e->ntx, 128, 0, s>>>(P, e->ts, e->cap, e->co, e->tr_begin, e->tr_end, e->acc_valid,
-                                                               e->g.x, e->g.y, e->g.vx, e->g.vy, e->g.ax, e->g.ay, e->g.id,
-                                                               e->g_cursor);
+    tile_gather_kernel<<<e->lrows_alloc * e->ntx, 128, 0, s>>>(P, e->acc, e->ts, e->cap, e->co, e->tr_begin, e->tr_end,
+                                                               e->acc_valid, e->g.x, e->g.y, e->g.vx, e->g.vy, e->g.ax,
+                                                               e->g.ay, e->g.id, e->g_cursor);
     ++sim->launches;
     PSIM_CUDA(cudaGetLastError());
     int n = 0;
