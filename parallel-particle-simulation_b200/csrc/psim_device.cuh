@@ -37,17 +37,33 @@ __device__ __forceinline__ int axis_cell(double v, int bincnt) {
     return min(max(c, 0), bincnt - 1);
 }
 
-// Both coordinates at once: one rare branch instead of two.
-__device__ __forceinline__ void cell_of(double x, double y, int bincnt, int& row, int& col) {
+// Both coordinates at once, one rare branch on the common path.  Also returns the unclamped floors (ix, iy)
+// of the products and their fractions (fx, fy), from which callers build an FP32 position in cell units.
+static __device__ __noinline__ int2 cell_of_exact(double x, double y, int bincnt) {
+    return make_int2(min(max(__double2int_rd(__ddiv_rn(x, kBin)), 0), bincnt - 1),
+                     min(max(__double2int_rd(__ddiv_rn(y, kBin)), 0), bincnt - 1));
+}
+__device__ __forceinline__ void cell_of_parts(double x, double y, int bincnt, int& row, int& col, int& ix, int& iy, double& fx,
+                                              double& fy) {
     const double tx = __dmul_rn(x, 100.0), ty = __dmul_rn(y, 100.0);
-    int cx = __double2int_rd(tx), cy = __double2int_rd(ty);
-    const double fx = __dsub_rn(tx, __int2double_rn(cx)), fy = __dsub_rn(ty, __int2double_rn(cy));
-    if (fmax(fabs(__dsub_rn(fx, 0.5)), fabs(__dsub_rn(fy, 0.5))) > 0.5 - 1e-9) {
-        cx = axis_cell_divide(x);
-        cy = axis_cell_divide(y);
+    ix = __double2int_rd(tx);
+    iy = __double2int_rd(ty);
+    fx = __dsub_rn(tx, __int2double_rn(ix));
+    fy = __dsub_rn(ty, __int2double_rn(iy));
+    row = ix;
+    col = iy;
+    // near a cell edge (or v == 0), or outside [0, bincnt): exact division and clamp
+    if (fmax(fabs(__dsub_rn(fx, 0.5)), fabs(__dsub_rn(fy, 0.5))) > 0.5 - 1e-9 || (unsigned)ix >= (unsigned)bincnt ||
+        (unsigned)iy >= (unsigned)bincnt) {
+        const int2 rc = cell_of_exact(x, y, bincnt);
+        row = rc.x;
+        col = rc.y;
     }
-    row = min(max(cx, 0), bincnt - 1);
-    col = min(max(cy, 0), bincnt - 1);
+}
+__device__ __forceinline__ void cell_of(double x, double y, int bincnt, int& row, int& col) {
+    int ix, iy;
+    double fx, fy;
+    cell_of_parts(x, y, bincnt, row, col, ix, iy, fx, fy);
 }
 
 // Rank of a neighbour cell (dr, dc) in the reference's visiting order

@@ -36,6 +36,7 @@
 // exports of one tile row are one contiguous byte range, so the halo exchange AND the particle
 // migration between GPUs are a single send/receive of the first / last owned row per neighbour.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "psim_force.cuh"
@@ -48,16 +49,16 @@ namespace psim {
 // compile-time tile configurations
 // ------------------------------------------------------------------------------------------
 // CAP slots per tile (mean population is 0.2*TS^2), HE / HC entries per edge / corner halo list,
-// CO outbox records per tile of which the first CS are staged in shared memory by the pipeline (a
-// tile that receives more from one neighbour reads the rest straight from global memory: this only
-// happens in bursts, e.g. a column of the initial lattice that sits exactly on a tile boundary),
+// CO outbox records per tile; the outboxes of the 3x3 tiles are staged in shared memory back to back, OS
+// records in total (a tile whose surroundings hold more reads the rest straight from global memory: this
+// only happens in bursts, e.g. a column of the initial lattice that sits exactly on a tile boundary),
 // NP pair-list entries, THREADS consumer threads per CTA (every CTA has one more warp, the producer),
 // CTAS resident per SM.  THREADS is a little above the MEAN population, so nearly every lane has a
 // particle in the first pass; the second pass (PER = 2) only runs for the slots past THREADS.
 template <int TS> struct TileCfg;
-template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 64, CS = 3, NP = 32,  THREADS = 64,  CTAS = 8; };
-template <> struct TileCfg<32> { static constexpr int CAP = 352,  HE = 32, HC = 8, CO = 64, CS = 4, NP = 96,  THREADS = 224, CTAS = 4; };
-template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 64, CS = 6, NP = 320, THREADS = 832, CTAS = 1; };
+template <> struct TileCfg<16> { static constexpr int CAP = 128,  HE = 24, HC = 8, CO = 64, OS = 24, NP = 32,  THREADS = 64,  CTAS = 8; };
+template <> struct TileCfg<32> { static constexpr int CAP = 352,  HE = 32, HC = 8, CO = 64, OS = 48, NP = 64,  THREADS = 224, CTAS = 4; };
+template <> struct TileCfg<64> { static constexpr int CAP = 1152, HE = 64, HC = 8, CO = 64, OS = 96, NP = 320, THREADS = 832, CTAS = 1; };
 
 struct __align__(16) OutRec {  // one migrating particle, 64 bytes
     double x, y, vx, vy, ax, ay;
@@ -68,18 +69,18 @@ struct __align__(16) OutRec {  // one migrating particle, 64 bytes
 static_assert(sizeof(OutRec) == 64, "OutRec must be 64 bytes");
 
 constexpr unsigned kEmpty = 0xFFFFu;          // end of a cell's list / empty cell
-constexpr float kPrefilter2 = 1.001e-4f;      // FP32 candidate test: cutoff^2 widened by 1e-3 (float error is < 1e-5)
+constexpr float kPrefilter2 = 1.001f;         // FP32 candidate test in cell units: cutoff^2 = 1 widened by 1e-3 (float error < 2e-5)
 
 template <int TS> struct TileDims {
     using C = TileCfg<TS>;
     static constexpr int W = TS + 2, NC = W * W;
     static constexpr int RW = (W + 31) / 32 + 1;          // occupancy words per cell row (+1: funnel shifts read one past)
     static constexpr int HL = 4 * C::HE + 4 * C::HC;      // halo entries a tile exports / stages
-    static constexpr int MAXH = HL + 32;                  // apron capacity (halo lists + apron outbox records)
+    static constexpr int MAXH = HL + 16;                  // apron capacity (halo lists + apron outbox records)
     static constexpr int PTOT = C::CAP + MAXH;
     static constexpr int PER = (C::CAP + C::THREADS - 1) / C::THREADS;
     static constexpr int NW = C::THREADS / 32;            // consumer warps
-    static constexpr int OS = 9 * C::CS;                  // staged outbox records
+    static constexpr int OS = C::OS;                      // staged outbox records (all nine outboxes together)
     static_assert(C::CAP % 4 == 0 && C::THREADS % 32 == 0 && NW <= 32 && PTOT < 0xFFFF, "configuration");
 };
 
@@ -98,20 +99,28 @@ template <int TS> struct __align__(16) TileSmem {
     using D = TileDims<TS>;
     Stage<TS> st[2];
     double2 pres[C::NP];                      // pair list: contribution of pair t to its first particle
-    float2 rel[D::PTOT];                      // tile-relative FP32 positions (prefilter only)
+    float2 rel[D::PTOT];                      // tile-relative FP32 positions in cell units (prefilter only; read before barrier 2,
+                                              // the producer writes the next tile's after it)
     unsigned head[2][D::NC];                  // per cell: first particle of its list (kEmpty: none); double buffered by tile
     unsigned rowbits[2][D::W * D::RW];        // per cell row: occupancy bit per cell
     unsigned pij[C::NP];                      // pair list: i | j << 16
-    unsigned long long full[2];               // mbarriers: stage filled by TMA (producer -> consumers)
-    unsigned long long empty[2];              // mbarriers: stage released (consumers -> producer)
-    unsigned short next[D::PTOT];             // next particle in the same cell
-    unsigned short pcell[2][D::PTOT];         // cell of a binned particle (0xFFFF: not binned); double buffered like head
-    int cnts[2][20];                          // staged tiles: [0] own, [1..8] halo lists, [9..17] outboxes, [18] halo total, [19] staged outbox records
+    unsigned long long full[2];               // mbarriers: stage filled by TMA
+    unsigned short next[2][D::PTOT];          // next particle in the same cell (double buffered like head: the exact path of
+                                              // a slow warp may still walk the lists while a fast warp bins the next tile)
+    unsigned short pcell[D::PTOT];            // cell of a binned particle (read before barrier 2, the producer writes the next
+                                              // tile's after it)
+    unsigned short pcode[C::CAP];             // per own particle: search result (pair count | pair-list base << 2), B -> D
+    int cnts[2][32];                          // staged tiles: [0] own, [1..8] halo lists, [9..17] outboxes, [18] halo total,
+                                              // [19] staged outbox records, [20..28] staged records per outbox
     int hout[8];
-    int n_own, n_apron, npairs, flags;
+    int n_own[2];                             // per stage: population after ingest
+    int prev_lr, prev_tc;                     // tile whose export counts still have to be published
+    int npairs, flags;
     int n_stay, n_leave;                      // stayers / leavers of the current tile (warp-aggregated atomics)
     int hw_leave, hw_halo, hw_tile, hw_apron;   // high-water marks over the tiles this CTA processed
 };
+
+static_assert(4 * (sizeof(TileSmem<32>) + 1024) <= 233472, "four CTAs of the 32-cell tile kernel must fit one SM's shared memory");
 
 __host__ __device__ inline int halo_offset(int list, int HE, int HC) { return list < 4 ? list * HE : 4 * HE + (list - 4) * HC; }
 __host__ __device__ inline int halo_cap(int list, int HE, int HC) { return list < 4 ? HE : HC; }
@@ -201,10 +210,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// barrier among the consumer threads only (id 1; id 0 is __syncthreads)
-template <int N>
-__device__ __forceinline__ void consumer_sync() {
-    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
+// named barrier `ID` among N threads (id 0 is __syncthreads)
+template <int ID, int N>
+__device__ __forceinline__ void named_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -248,11 +257,17 @@ struct TileWalker {
     }
 };
 
-// list count j of tile t: j = 0 own population, 1..8 apron sources, 9..17 outboxes of the 3x3 tiles
+// list count j of tile t: j = 0 own population, 1..8 apron sources, 9..17 outboxes of the 3x3 tiles.
+// Returns the RAW stored value (clamp_count applies the capacity later) so that nothing depends on the
+// global load until the caller needs the number.
+template <int TS>
+__device__ __forceinline__ int clamp_count(int raw, int j) {
+    using C = TileCfg<TS>;
+    return min(raw, j == 0 ? C::CAP : j >= 9 ? C::CO : j <= 4 ? C::HE : C::HC);
+}
 template <int TS>
 __device__ __forceinline__ int load_count(const TileParams& P, const TileCoord& c, int j) {
-    using C = TileCfg<TS>;
-    if (j == 0) return min(P.tcount[c.lt], C::CAP);
+    if (j == 0) return P.tcount[c.lt];
     int dr, dc, list;
     if (j <= 8) {
         halo_source(j - 1, dr, dc, list);
@@ -264,21 +279,22 @@ __device__ __forceinline__ int load_count(const TileParams& P, const TileCoord& 
     const int ntr = c.tr + dr, ntc = c.tc + dc;
     if (ntr < 0 || ntr >= P.nty || ntc < 0 || ntc >= P.ntx) return 0;
     const int* ec = reinterpret_cast<const int*>(row_ptr(P.exp_in, P.L, c.lr + dr) + P.L.off_cnt) + (size_t)ntc * 16;
-    return min(ec[list], list == 8 ? C::CO : halo_cap(list, C::HE, C::HC));
+    return ec[list];
 }
 
-// Producer: fetch the list counts of tile t, publish them in `cnt`, issue the bulk copies into `st`.
+// Loader (one warp): given the list counts of a tile (lane j holds count j, fetched earlier so that the
+// global-load latency is hidden), publish them in `cnt` and issue the bulk copies into `st`.
 //   copy 0 pos, 1 vel, 2 id, 3..10 apron source k = copy-3 (straight to its final place behind the own
 //   particles), 11..19 outbox nb = copy-11 (first CS records, packed back to back)
 template <int TS>
-__device__ __forceinline__ void produce_tile(const TileParams& P, const TileCoord c, Stage<TS>& st, int* cnt, unsigned long long* bar,
-                                             unsigned long long* empty_bar, bool wait_empty, unsigned empty_parity, int lane) {
+__device__ __forceinline__ void issue_tile(const TileParams& P, const TileCoord c, Stage<TS>& st, int* cnt, unsigned long long* bar,
+                                           int cj_raw, int lane) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    const int cj = lane < 18 ? load_count<TS>(P, c, lane) : 0;
+    const int cj = lane < 18 ? clamp_count<TS>(cj_raw, lane) : 0;
     // exclusive prefixes: halo entries over lanes 1..8, staged outbox records over lanes 9..17
     const int hv = (lane >= 1 && lane <= 8) ? cj : 0;
-    const int ov = (lane >= 9 && lane <= 17) ? min(cj, C::CS) : 0;
+    const int ov = (lane >= 9 && lane <= 17) ? cj : 0;
     int hs = hv, os = ov;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -288,17 +304,19 @@ __device__ __forceinline__ void produce_tile(const TileParams& P, const TileCoor
             os += b;
         }
     }
-    const int n_halo = __shfl_sync(0xffffffffu, hs, 8), n_staged = __shfl_sync(0xffffffffu, os, 17);
+    const int n_halo = __shfl_sync(0xffffffffu, hs, 8), n_staged = min(__shfl_sync(0xffffffffu, os, 17), D::OS);
+    const int staged = max(0, min(ov, D::OS - (os - ov)));   // lanes 9..17: records of my outbox that fit the staging area
     const int n = __shfl_sync(0xffffffffu, cj, 0);
     // what this lane copies
     const int src_lane = lane < 3 ? 0 : lane < 11 ? lane - 2 : lane < 20 ? lane - 2 : 0;   // lane holding the count of my copy
     const int my_cnt = __shfl_sync(0xffffffffu, cj, src_lane);
     const int my_hoff = __shfl_sync(0xffffffffu, hs - hv, src_lane);
     const int my_ooff = __shfl_sync(0xffffffffu, os - ov, src_lane);
-    if (wait_empty) mbar_wait_relaxed(empty_bar, empty_parity);   // the tile two iterations back has left the stage
+    const int my_staged = __shfl_sync(0xffffffffu, staged, src_lane);
     if (lane < 18) cnt[lane] = cj;
     if (lane == 18) cnt[18] = n_halo;
     if (lane == 19) cnt[19] = n_staged;
+    if (lane >= 9 && lane <= 17) cnt[11 + lane] = staged;
     const size_t gbase = (size_t)c.lt * C::CAP;
     const void* src = nullptr;
     void* dst = nullptr;
@@ -321,7 +339,7 @@ __device__ __forceinline__ void produce_tile(const TileParams& P, const TileCoor
     } else if (lane < 20) {
         const int nb = lane - 11;
         const int dr = nb / 3 - 1, dc = nb % 3 - 1;
-        bytes = (unsigned)min(my_cnt, C::CS) * (unsigned)sizeof(OutRec);
+        bytes = (unsigned)my_staged * (unsigned)sizeof(OutRec);
         if (bytes) {
             src = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, c.lr + dr) + P.L.off_obox) + (size_t)(c.tc + dc) * C::CO;
             dst = st.obox + my_ooff;
@@ -360,20 +378,63 @@ static __device__ __noinline__ double2 slow_force(const double2* xy, const unsig
     return make_double2(ax, ay);
 }
 
+#ifdef PSIM_PHASE_TIMERS
+// profiling build only: cycles spent per phase, summed over tiles, for warp 0, a middle warp and the loader warp
+__device__ unsigned long long g_phase_cycles[34][12];
+__device__ unsigned g_hist[4][64];   // histograms (256-cycle bins) of per-warp per-tile durations: 0 A, 1 B, 2 DE, 3 top+wait
+#define PSIM_HIST(h, k) do { if (lane == 0) atomicAdd(&g_hist[h][min((tacc[k] - hprev[k]) >> 8, 63u)], 1u); hprev[k] = tacc[k]; } while (0)
+#define PSIM_TICK(k)                                   \
+    do {                                               \
+        /* a barrier only blocks at the next access to shared memory: force one before reading the clock */ \
+        asm volatile("" ::"r"(*(volatile int*)&S.flags) : "memory"); \
+        const unsigned now__ = (unsigned)clock();      \
+        tacc[k] += now__ - tlast;                      \
+        tlast = now__;                                 \
+    } while (0)
+#else
+#define PSIM_TICK(k) do {} while (0)
+#define PSIM_HIST(h, k) do {} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // the per-step kernel
 // ------------------------------------------------------------------------------------------
+// Bin particle p of stage sb: exact cell, FP32 position in cell units relative to the table origin (cell
+// (r0-1, c0-1); integer part from the unclamped floor, fraction from the exact product: error < 4e-6 cells),
+// list head exchange, occupancy bit.  `ring_check`: apron entries may lie outside the table (never for the
+// lists of proper neighbours; kept as a memory-safety guard).
+template <int TS, bool kRingCheck>
+__device__ __forceinline__ void bin_particle(TileSmem<TS>& S, int sb, int p, double x, double y, int r0m1, int c0m1, int bincnt) {
+    using D = TileDims<TS>;
+    int row, col, ix, iy;
+    double fx, fy;
+    cell_of_parts(x, y, bincnt, row, col, ix, iy, fx, fy);
+    const int lrow = row - r0m1, lcol = col - c0m1;
+    if (kRingCheck && ((unsigned)lrow >= (unsigned)D::W || (unsigned)lcol >= (unsigned)D::W)) return;
+    const int cell = lrow * D::W + lcol;
+    const unsigned old = atomicExch(&S.head[sb][cell], (unsigned)p);
+    S.next[sb][p] = (unsigned short)old;
+    S.pcell[p] = (unsigned short)cell;
+    atomicOr(&S.rowbits[sb][lrow * D::RW + (lcol >> 5)], 1u << (lcol & 31));
+    S.rel[p] = make_float2(__int2float_rn(ix - r0m1) + __double2float_rn(fx), __int2float_rn(iy - c0m1) + __double2float_rn(fy));
+}
+
 template <int TS, bool kStoreAcc>
 __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) tile_step_kernel(const TileParams P) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, NC = D::NC, PER = D::PER, RW = D::RW, NW = D::NW;
+    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, NC = D::NC, RW = D::RW, NW = D::NW;
     constexpr int HE = C::HE, HC = C::HC, CO = C::CO, NP = C::NP;
+    // named barriers: 1 = cell table complete (consumers + producer), 2 = pair list complete (consumers),
+    // 3 = pair contributions ready and the other cell table clean (consumers + producer)
+    constexpr int kBarTable = 1, kBarPairs = 2, kBarForces = 3;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem<TS>& S = *reinterpret_cast<TileSmem<TS>*>(smem_raw);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));   // volatile: keep it in a register instead of re-reading the special register
+    const int lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
     const int first = blockIdx.x;
     if (first >= P.ntiles) return;
@@ -382,107 +443,57 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
     if (tid == 0) {
         mbar_init(&S.full[0], 1);
         mbar_init(&S.full[1], 1);
-        mbar_init(&S.empty[0], NW);
-        mbar_init(&S.empty[1], NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.npairs = 0;
         S.flags = 0;
         S.n_stay = S.n_leave = 0;
         S.hw_leave = S.hw_halo = S.hw_tile = S.hw_apron = 0;
+        S.prev_lr = -1;
+        S.prev_tc = 0;
     }
     if (tid < 8) S.hout[tid] = 0;
     for (int c = tid; c < 2 * NC; c += T + 32) (&S.head[0][0])[c] = kEmpty;
     for (int c = tid; c < 2 * W * RW; c += T + 32) (&S.rowbits[0][0])[c] = 0u;
     __syncthreads();
 
-    // ---- producer warp: runs up to two tiles ahead of the consumers ----------------------------------
     TileWalker walk;
     walk.init(P, first, G);
+
+    // =================================================================================================
+    // producer warp: feeds the two-stage pipeline one tile ahead, ingests the migrants and bins the apron of
+    // the next tile.  It sleeps in the hardware barriers the consumers pass anyway, so it costs no issue
+    // slots while idle.
+    // =================================================================================================
     if (warp == NW) {
-        for (int j = 0;; ++j) {
-            const int t = first + j * G;
-            if (t >= P.ntiles) break;
-            produce_tile<TS>(P, walk.coord(P), S.st[j & 1], S.cnts[j & 1], &S.full[j & 1], &S.empty[j & 1], j >= 2,
-                             (unsigned)(((j >> 1) - 1) & 1), lane);
-            walk.advance(P);
-        }
-        return;
-    }
-
-    // ---- consumers ----------------------------------------------------------------------------------
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int prev_lr = -1, prev_tc = 0;   // tile whose halo-list counts still have to be published
-    auto publish_halo_counts = [&](int done_lr, int done_tc) {
-        // tid < 8: list `tid` of that tile is complete (all appends happened before the last barrier)
-        int* ec = reinterpret_cast<int*>(row_ptr(P.exp_out, P.L, done_lr) + P.L.off_cnt) + (size_t)done_tc * 16;
-        const int k = S.hout[tid], cap = halo_cap(tid, HE, HC);
-        if (k > cap) atomicOr(&S.flags, kErrHaloOverflow);
-        ec[tid] = min(k, cap);
-        S.hout[tid] = 0;
-        if (tid < 4) atomicMax(&S.hw_halo, k);
-    };
-
-    for (int it = 0;; ++it) {
-        const int t = first + it * G;
-        if (t >= P.ntiles) break;
-        const int sb = it & 1;   // stage and cell-table buffer of this tile
-        Stage<TS>& st = S.st[sb];
-        const int* cnt = S.cnts[sb];
-        unsigned* head = S.head[sb];
-        unsigned* rowbits = S.rowbits[sb];
-        unsigned short* pcell = S.pcell[sb];
-        const TileCoord tc_ = walk.coord(P);
-        const int tr = tc_.tr, tc = tc_.tc, lt = tc_.lt, lr = tc_.lr;
-        const int r0 = tr * TS, c0 = tc * TS;
-        const size_t gbase = (size_t)lt * CAP;
-        const double ox = (double)(r0 - 1) * kBin, oy = (double)(c0 - 1) * kBin;   // origin of the tile-relative FP32 frame
-
-        mbar_wait(&S.full[sb], (unsigned)((it >> 1) & 1));  // this tile's bytes (and counts) have landed
-
-        const int n_own0 = cnt[0], n_halo = cnt[18];
-
-        // bin particle p (index into st.xy) that lies in local cell (lrow, lcol) of the (TS+2)^2 table
-        auto bin = [&](int p, int lrow, int lcol, double x, double y) {
-            const int cell = lrow * W + lcol;
-            const unsigned old = atomicExch(&head[cell], (unsigned)p);
-            S.next[p] = (unsigned short)old;
-            pcell[p] = (unsigned short)cell;
-            atomicOr(&rowbits[lrow * RW + (lcol >> 5)], 1u << (lcol & 31));
-            S.rel[p] = make_float2(__double2float_rn(__dsub_rn(x, ox)), __double2float_rn(__dsub_rn(y, oy)));
-        };
-
-        // ---- A: ingest newcomers, bin own + apron particles ---------------------------------------------
-        if (warp == 0) {
-            // outbox records of the 3x3 tiles: records now in my tile are appended to my stripe, records in my
-            // apron ring become apron particles (after the halo-list entries).  One lane per record.
-            int n_own = n_own0, n_ap = n_halo, flags = 0;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        // Ingest: outbox records of the 3x3 tiles around tile c (staged in stage sb).  Records now inside the
+        // tile are appended to its stripe, records in its apron ring become apron particles (after the
+        // halo-list entries).  One lane per record.  Runs while the consumers still work on the previous tile.
+        auto ingest = [&](int sb, const TileCoord c, unsigned full_parity) {
+            Stage<TS>& st = S.st[sb];
+            const int* cnt = S.cnts[sb];
+            mbar_wait_relaxed(&S.full[sb], full_parity);
+            const int r0 = c.tr * TS, c0 = c.tc * TS;
+            int n_own = cnt[0], n_ap = cnt[18], flags = 0;
             auto take = [&](bool valid, const OutRec* rec) {
                 bool mine = false, apron = false;
-                int lrow = 0, lcol = 0;
                 if (valid) {
-                    lrow = rec->row - (r0 - 1);
-                    lcol = rec->col - (c0 - 1);
+                    const int lrow = rec->row - (r0 - 1), lcol = rec->col - (c0 - 1);
                     const bool ring = lrow >= 0 && lrow <= TS + 1 && lcol >= 0 && lcol <= TS + 1;
                     mine = lrow >= 1 && lrow <= TS && lcol >= 1 && lcol <= TS;
                     apron = ring && !mine;
                 }
                 const unsigned mm = __ballot_sync(0xffffffffu, mine), am = __ballot_sync(0xffffffffu, apron);
-                if (mine) {
-                    const int d = n_own + __popc(mm & lt_mask);
-                    if (d < CAP) {
+                if (mine | apron) {
+                    const int d = mine ? n_own + __popc(mm & lt_mask) : CAP + n_ap + __popc(am & lt_mask);
+                    if (d < (mine ? CAP : D::PTOT)) {
                         const double x = rec->x, y = rec->y;
                         st.xy[d] = make_double2(x, y);
-                        st.v[d] = make_double2(rec->vx, rec->vy);
-                        st.id[d] = rec->id;
-                        bin(d, lrow, lcol, x, y);
-                    }
-                }
-                if (apron) {
-                    const int hh = n_ap + __popc(am & lt_mask);
-                    if (hh < D::MAXH) {
-                        const double x = rec->x, y = rec->y;
-                        st.xy[CAP + hh] = make_double2(x, y);
-                        bin(CAP + hh, lrow, lcol, x, y);
+                        if (mine) {
+                            st.v[d] = make_double2(rec->vx, rec->vy);
+                            st.id[d] = rec->id;
+                        }
+                        bin_particle<TS, true>(S, sb, d, x, y, r0 - 1, c0 - 1, P.bincnt);
                     }
                 }
                 n_own += __popc(mm);
@@ -491,96 +502,173 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             const int n_staged = cnt[19];
 #pragma unroll 1
             for (int q0 = 0; q0 < n_staged; q0 += 32) take(q0 + lane < n_staged, &st.obox[min(q0 + lane, D::OS - 1)]);
-            int beyond = 0;
-#pragma unroll
-            for (int nb = 0; nb < 9; ++nb) beyond |= cnt[9 + nb] > C::CS;
-            if (beyond) {
-                // bursts only: records past the staged CS are read from the neighbour's outbox in global memory
+            if (n_staged == D::OS) {
+                // bursts only: records that did not fit the staging area are read from the neighbours' outboxes in global memory
 #pragma unroll 1
                 for (int nb = 0; nb < 9; ++nb) {
-                    const int c = cnt[9 + nb];
-                    if (c <= C::CS) continue;
-                    const OutRec* grec = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, lr + nb / 3 - 1) + P.L.off_obox) +
-                                         (size_t)(tc + nb % 3 - 1) * CO;
-                    for (int e0 = C::CS; e0 < c; e0 += 32) take(e0 + lane < c, grec + min(e0 + lane, c - 1));
+                    const int n = cnt[9 + nb], s0 = cnt[20 + nb];
+                    if (n <= s0) continue;
+                    const OutRec* grec = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, c.lr + nb / 3 - 1) + P.L.off_obox) +
+                                         (size_t)(c.tc + nb % 3 - 1) * CO;
+                    for (int e0 = s0; e0 < n; e0 += 32) take(e0 + lane < n, grec + min(e0 + lane, n - 1));
+                }
+            }
+            // the halo-list apron (already in place behind the own particles)
+            {
+                const int n_halo = cnt[18];
+#pragma unroll 1
+                for (int q = lane; q < n_halo; q += 32) {
+                    const double2 a = st.xy[CAP + q];
+                    bin_particle<TS, true>(S, sb, CAP + q, a.x, a.y, r0 - 1, c0 - 1, P.bincnt);
                 }
             }
             if (n_own > CAP) { flags |= kErrTileOverflow; n_own = CAP; }
             if (n_ap > D::MAXH) { flags |= kErrSmemOverflow; n_ap = D::MAXH; }
             if (lane == 0) {
-                S.n_own = n_own;
-                S.n_apron = n_ap;
+                S.n_own[sb] = n_own;
+                S.hw_tile = max(S.hw_tile, n_own);
+                S.hw_apron = max(S.hw_apron, n_ap);
                 if (flags) atomicOr(&S.flags, flags);
             }
-        }
-        // own particles that were already here and the halo-list apron
-        for (int q = tid; q < n_own0 + n_halo; q += T) {
-            const int p = q < n_own0 ? q : CAP + (q - n_own0);
-            const double2 a = st.xy[p];
-            int lrow, lcol;
-            cell_of(a.x, a.y, P.bincnt, lrow, lcol);
-            lrow -= r0 - 1;
-            lcol -= c0 - 1;
-            if (lrow >= 0 && lrow < W && lcol >= 0 && lcol < W) bin(p, lrow, lcol, a.x, a.y);
-            else pcell[p] = 0xFFFFu;
-        }
-        consumer_sync<T>();   // (1) cell table complete
-        if (prev_lr >= 0 && tid < 8) publish_halo_counts(prev_lr, prev_tc);
-        const int n_own = S.n_own, n_apron = S.n_apron;
+            fence_proxy_async();   // my generic writes to this stage are ordered before the bulk copies that refill it
+            __syncwarp();
+        };
 
-        // ---- B: candidate search in FP32 ------------------------------------------------------------------
-        int pb[PER];   // fc (0, 1, 2; 3 = exact path) | pair-list base << 2
-#pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int i = r * T + tid;
-            pb[r] = 0;
-            if (i < n_own) {
-                const int cell = pcell[i];
-                const int lrow = cell / W, lcol = cell - lrow * W;
-                const float2 ri = S.rel[i];
-                // 9 occupancy bits of the 3x3 neighbourhood, bit 3*(dr+1) + (dc+1)
-                const unsigned* rb = rowbits + (lrow - 1) * RW + ((lcol - 1) >> 5);
-                const unsigned sh = (unsigned)(lcol - 1) & 31u;
-                unsigned m = 0;
-#pragma unroll
-                for (int dr = 0; dr < 3; ++dr) m |= (__funnelshift_r(rb[dr * RW], rb[dr * RW + 1], sh) & 7u) << (3 * dr);
-                if (head[cell] == (unsigned)i && S.next[i] == kEmpty) m &= ~16u;   // alone in my own cell
-                int fc = 0;
-                unsigned cand = 0;   // the last two prefilter hits, 16 bits each
-                while (m) {
-                    const int k = __ffs((int)m) - 1;
-                    m &= m - 1;
-                    const int q = (k * 11) >> 5;   // k / 3
-                    unsigned h = head[cell + q * (W - 3) + k - (W + 1)];
-                    do {   // the occupancy bit guarantees a non-empty list
-                        const float2 rj = S.rel[h];
-                        const unsigned hn = S.next[h];
-                        const float dx = rj.x - ri.x, dy = rj.y - ri.y;
-                        const float r2 = dx * dx + dy * dy;
-                        if (r2 <= kPrefilter2 && h != (unsigned)i) {
-                            cand = (cand << 16) | h;
-                            ++fc;
-                        }
-                        h = hn;
-                    } while (h != kEmpty);
-                }
-                if (fc >= 3) {
-                    pb[r] = 3;
-                } else if (fc > 0) {
-                    const int base = atomicAdd(&S.npairs, fc);
-                    if (base + fc <= NP) {
-                        S.pij[base] = (unsigned)i | (cand << 16);
-                        if (fc == 2) S.pij[base + 1] = (unsigned)i | (cand & 0xFFFF0000u);
-                        pb[r] = fc | (base << 2);
-                    } else {
-                        pb[r] = 3;
-                    }
-                }
+        issue_tile<TS>(P, walk.coord(P), S.st[0], S.cnts[0], &S.full[0], lane < 18 ? load_count<TS>(P, walk.coord(P), lane) : 0, lane);
+        ingest(0, walk.coord(P), 0u);
+        for (int it = 0;; ++it) {
+            const int t = first + it * G;
+            if (t >= P.ntiles) break;
+            const int sb = it & 1;
+            const bool has_next = t + G < P.ntiles;
+            walk.advance(P);   // -> tile it + 1
+            const TileCoord cn = walk.coord(P);
+            int cj_next = 0;
+            if (has_next && lane < 18) cj_next = load_count<TS>(P, cn, lane);   // in flight across the barrier
+            named_sync<kBarTable, T + 32>();   // every consumer warp has left tile it - 1: its stage is free
+            if (has_next) issue_tile<TS>(P, cn, S.st[sb ^ 1], S.cnts[sb ^ 1], &S.full[sb ^ 1], cj_next, lane);
+            named_sync<kBarForces, T + 32>();  // the consumers have cleaned the other cell table and are done with rel / pcell
+            if (has_next) ingest(sb ^ 1, cn, (unsigned)(((it + 1) >> 1) & 1));
+        }
+        return;
+    }
+
+    // =================================================================================================
+    // consumer warps
+    // =================================================================================================
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // Deferred bookkeeping of the tile that was just finished, run by nine threads right after a barrier
+    // (all appends / slot reservations of that tile happened before it): tid < 8 publishes halo list `tid`,
+    // tid == 8 the outbox count and the tile's new population.
+    auto publish_counts = [&]() {
+        const int done_lr = S.prev_lr, done_tc = S.prev_tc;
+        if (done_lr < 0) return;
+        int* ec = reinterpret_cast<int*>(row_ptr(P.exp_out, P.L, done_lr) + P.L.off_cnt) + (size_t)done_tc * 16;
+        if (tid < 8) {
+            const int k = S.hout[tid], cap = halo_cap(tid, HE, HC);
+            if (k > cap) atomicOr(&S.flags, kErrHaloOverflow);
+            ec[tid] = min(k, cap);
+            S.hout[tid] = 0;
+            if (tid < 4) atomicMax(&S.hw_halo, k);
+        } else {
+            const int n_stay = S.n_stay, n_leave = S.n_leave;
+            S.n_stay = 0;
+            S.n_leave = 0;
+            if (n_leave > CO) atomicOr(&S.flags, kErrOutboxOverflow);
+            ec[8] = min(n_leave, CO);
+            P.tcount[done_lr * P.ntx + done_tc] = n_stay;
+            S.hw_leave = max(S.hw_leave, n_leave);
+        }
+    };
+
+#ifdef PSIM_PHASE_TIMERS
+    unsigned tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned hprev[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned tlast = (unsigned)clock();
+#endif
+    for (int it = 0;; ++it) {
+        if (first + it * G >= P.ntiles) break;
+        const int sb = it & 1;   // stage and cell-table buffer of this tile
+        Stage<TS>& st = S.st[sb];
+        const unsigned* head = S.head[sb];
+        const unsigned short* next = S.next[sb];
+        const int lr = walk.lr, tc = walk.tc, tr = P.tr_base + lr;
+        const int r0 = tr * TS, c0 = tc * TS;
+
+        PSIM_TICK(0);
+        mbar_wait(&S.full[sb], (unsigned)((it >> 1) & 1));  // this tile's bytes (and counts) have landed
+        PSIM_TICK(1);
+
+        // ---- A: bin the particles that were already here (the producer warp bins the migrants and the apron
+        //      concurrently; the table only takes atomics) ------------------------------------------------------
+        {
+            const int n_own0 = S.cnts[sb][0];
+#pragma unroll 1
+            for (int p = tid; p < n_own0; p += T) {
+                const double2 a = st.xy[p];
+                bin_particle<TS, false>(S, sb, p, a.x, a.y, r0 - 1, c0 - 1, P.bincnt);
             }
         }
-        consumer_sync<T>();   // (2) pair list complete
+        PSIM_TICK(2);
+        named_sync<kBarTable, T + 32>();   // (1) cell table complete; every warp has left the previous tile
+        PSIM_TICK(3);
+        if (tid < 9) publish_counts();
+        const int n_own = S.n_own[sb];
 
-        // ---- C: exact pair evaluation, one lane per pair (the last warps first: they have the fewest particles) ----
+        // ---- B: candidate search in FP32 ------------------------------------------------------------------
+#pragma unroll 1
+        for (int i = tid; i < n_own; i += T) {
+            const int cell = S.pcell[i];
+            const int lrow = cell / W, lcol = cell - lrow * W;
+            const float2 ri = S.rel[i];
+            // 9 occupancy bits of the 3x3 neighbourhood, bit 3*(dr+1) + (dc+1)
+            const unsigned* rb = S.rowbits[sb] + (lrow - 1) * RW + ((lcol - 1) >> 5);
+            const unsigned sh = (unsigned)(lcol - 1) & 31u;
+            unsigned m = 0;
+#pragma unroll
+            for (int dr = 0; dr < 3; ++dr) m |= (__funnelshift_r(rb[dr * RW], rb[dr * RW + 1], sh) & 7u) << (3 * dr);
+            if (head[cell] == (unsigned)i && next[i] == kEmpty) m &= ~16u;   // alone in my own cell
+            int fc = 0;
+            unsigned cand = 0;   // the last two prefilter hits, 16 bits each
+            while (m) {
+                const int k = __ffs((int)m) - 1;
+                m &= m - 1;
+                const int q = (k * 11) >> 5;   // k / 3
+                unsigned h = head[cell + q * (W - 3) + k - (W + 1)];
+                do {   // the occupancy bit guarantees a non-empty list
+                    const float2 rj = S.rel[h];
+                    const unsigned hn = next[h];
+                    const float dx = rj.x - ri.x, dy = rj.y - ri.y;
+                    const float r2 = dx * dx + dy * dy;
+                    if (r2 <= kPrefilter2 && h != (unsigned)i) {
+                        cand = (cand << 16) | h;
+                        ++fc;
+                    }
+                    h = hn;
+                } while (h != kEmpty);
+            }
+            // code: fc (0, 1, 2; 3 = exact path) | pair-list base << 2
+            unsigned code = 0;
+            if (fc >= 3) {
+                code = 3;
+            } else if (fc > 0) {
+                const int base = atomicAdd(&S.npairs, fc);
+                if (base + fc <= NP) {
+                    S.pij[base] = (unsigned)i | (cand << 16);
+                    if (fc == 2) S.pij[base + 1] = (unsigned)i | (cand & 0xFFFF0000u);
+                    code = (unsigned)fc | ((unsigned)base << 2);
+                } else {
+                    code = 3;
+                }
+            }
+            S.pcode[i] = (unsigned short)code;
+        }
+        PSIM_TICK(4);
+        named_sync<kBarPairs, T>();   // (2) pair list complete
+        PSIM_TICK(5);
+
+        // ---- C: exact pair evaluation, one lane per pair (the last warps first: they have the fewest particles);
+        //      everybody else cleans the other cell table (last read before barrier 1) for the next tile ----------
         {
             const int np = min(S.npairs, NP);
             for (int u = T - 1 - tid; u < np; u += T) {
@@ -592,147 +680,125 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 if (!(r2 > kCutoff2) && r2 != 0.0) pair_contrib(dx, dy, r2, cx, cy);
                 S.pres[u] = make_double2(cx, cy);   // (+0, +0) for a prefilter false positive: neutral in the sum
             }
+            unsigned* oh = S.head[sb ^ 1];
+            unsigned* ob = S.rowbits[sb ^ 1];
+#pragma unroll 1
+            for (int c = tid; c < NC; c += T) oh[c] = kEmpty;
+#pragma unroll 1
+            for (int c = tid; c < W * RW; c += T) ob[c] = 0u;
         }
-        consumer_sync<T>();   // (3) contributions ready
+        PSIM_TICK(6);
+        named_sync<kBarForces, T + 32>();   // (3) contributions ready, other table clean
+        PSIM_TICK(7);
+        if (tid == 0) {
+            S.npairs = 0;   // next appended to after barrier 1 of the next tile
+            S.prev_lr = lr;
+            S.prev_tc = tc;
+        }
 
-        // ---- D: sum, move, new cell, stay / leave ----------------------------------------------------------------
-        double nx[PER], ny[PER], nax[kStoreAcc ? PER : 1], nay[kStoreAcc ? PER : 1];
-        int nrc[PER];  // new cell row << 16 | new cell column
-        int dst[PER];  // stayer: slot in the output stripe; leaver: -1 - outbox rank
-#pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int i = r * T + tid;
-            nrc[r] = 0;
-            dst[r] = 0;
-            nx[r] = ny[r] = 0.0;
-            bool stay = false, leave = false;
-            if (i < n_own) {
-                double ax = 0.0, ay = 0.0;
-                const int code = pb[r], fc = code & 3;
-                if (fc == 3) {
-                    const double2 a = slow_force<W>(st.xy, head, S.next, i, pcell[i]);
+        // ---- D: sum, move, new cell; E: re-tile (stayers -> other stripe buffer, leavers -> outbox, boundary
+        //      cells -> halo lists).  No barrier in between: slots come from warp-aggregated atomics. -----------
+        const size_t gbase = (size_t)(lr * P.ntx + tc) * CAP;
+#pragma unroll 1
+        for (int i0 = 0; i0 < n_own; i0 += T) {   // uniform trip count: the ballots below need whole warps
+            const int i = i0 + tid;
+            const bool valid = i < n_own;
+            double x = 0.0, y = 0.0, ax = 0.0, ay = 0.0;
+            double2 v = make_double2(0.0, 0.0);
+            int nrow = 0, ncol = 0, id = 0;
+            bool stay = false;
+            if (valid) {
+                const unsigned code = S.pcode[i], fc = code & 3u;
+                const double2 p = st.xy[i];
+                v = st.v[i];
+                id = st.id[i];
+                x = p.x;
+                y = p.y;
+                if (fc == 3u) {
+                    // (the cell is recomputed: pcell may already hold the next tile's entries)
+                    int srow, scol;
+                    cell_of(x, y, P.bincnt, srow, scol);
+                    const double2 a = slow_force<W>(st.xy, head, next, i, (srow - (r0 - 1)) * W + (scol - (c0 - 1)));
                     ax = a.x;
                     ay = a.y;
-                } else if (fc > 0) {
+                } else if (fc != 0u) {
                     const double2 c0_ = S.pres[code >> 2];
                     ax = __dadd_rn(ax, c0_.x);
                     ay = __dadd_rn(ay, c0_.y);
-                    if (fc == 2) {
+                    if (fc == 2u) {
                         const double2 c1_ = S.pres[(code >> 2) + 1];
                         ax = __dadd_rn(ax, c1_.x);
                         ay = __dadd_rn(ay, c1_.y);
                     }
                 }
-                const double2 p = st.xy[i];
-                double2 v = st.v[i];
-                double x = p.x, y = p.y;
                 move_particle(x, y, v.x, v.y, ax, ay, P.size);
-                nx[r] = x; ny[r] = y;
-                st.v[i] = v;   // only the owner reads it again
-                if (kStoreAcc) { nax[r] = ax; nay[r] = ay; }
-                int nrow, ncol;
                 cell_of(x, y, P.bincnt, nrow, ncol);
-                nrc[r] = (nrow << 16) | ncol;
-                const unsigned er = (unsigned)(nrow - r0), ec = (unsigned)(ncol - c0);
-                stay = er < (unsigned)TS && ec < (unsigned)TS;
-                leave = !stay;
+                stay = (unsigned)(nrow - r0) < (unsigned)TS && (unsigned)(ncol - c0) < (unsigned)TS;
             }
-            if (r * T < n_own) {   // warp-uniform: this pass has particles
-                // destination slots: one atomic per warp, lanes take consecutive slots after the warp's base
-                const unsigned sm = __ballot_sync(0xffffffffu, stay), lm = __ballot_sync(0xffffffffu, leave);
-                int sbase = 0, lbase = 0;
-                if (lane == 0) {
-                    if (sm) sbase = atomicAdd(&S.n_stay, __popc(sm));
-                    if (lm) lbase = atomicAdd(&S.n_leave, __popc(lm));
-                }
-                sbase = __shfl_sync(0xffffffffu, sbase, 0);
-                lbase = __shfl_sync(0xffffffffu, lbase, 0);
-                dst[r] = stay ? sbase + __popc(sm & lt_mask) : leave ? -1 - (lbase + __popc(lm & lt_mask)) : 0;
+            // destination slots: one atomic per warp, lanes take consecutive slots after the warp's base
+            const unsigned sm = __ballot_sync(0xffffffffu, stay), lm = __ballot_sync(0xffffffffu, valid && !stay);
+            int sbase = 0, lbase = 0;
+            if (lane == 0) {
+                if (sm) sbase = atomicAdd(&S.n_stay, __popc(sm));
+                if (lm) lbase = atomicAdd(&S.n_leave, __popc(lm));
             }
-        }
-        consumer_sync<T>();   // (4) warp counts published; nobody reads the cell table or the positions any more
-
-        // ---- E: re-tile ---------------------------------------------------------------------------------
-        char* orow = row_ptr(P.exp_out, P.L, lr);
-        double2* ohxy = reinterpret_cast<double2*>(orow + P.L.off_hxy) + (size_t)tc * D::HL;
-        OutRec* oobox = reinterpret_cast<OutRec*>(orow + P.L.off_obox) + (size_t)tc * CO;
-        int tflags = 0;
-#pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int i = r * T + tid;
-            if (i < n_own) {
-                const int nrow = nrc[r] >> 16, ncol = nrc[r] & 0xFFFF;
+            sbase = __shfl_sync(0xffffffffu, sbase, 0);
+            if (lm) lbase = __shfl_sync(0xffffffffu, lbase, 0);
+            if (stay) {
+                const double2 q = make_double2(x, y);
+                const size_t d = gbase + (size_t)(sbase + __popc(sm & lt_mask));
+                P.pos_out[d] = q;
+                P.vel_out[d] = v;
+                P.id_out[d] = id;
+                if (kStoreAcc) P.acc_out[d] = make_double2(ax, ay);
+                // boundary cells: append to the edge list(s) and, in a corner cell, the corner list
+                // (with TS >= 3 a cell is on at most one of N/S and one of W/E)
                 const int er = nrow - r0, ec = ncol - c0;
-                const double2 nv = st.v[i];
-                const double2 q = make_double2(nx[r], ny[r]);
-                head[pcell[i]] = kEmpty;   // leave the cell table clean for the tile after next
-                if (dst[r] >= 0) {
-                    const size_t d = gbase + (size_t)dst[r];
-                    P.pos_out[d] = q;
-                    P.vel_out[d] = nv;
-                    P.id_out[d] = st.id[i];
-                    if (kStoreAcc) P.acc_out[d] = make_double2(nax[kStoreAcc ? r : 0], nay[kStoreAcc ? r : 0]);
-                    // boundary cells: append to the edge list(s) and, in a corner cell, the corner list
-                    // (with TS >= 3 a cell is on at most one of N/S and one of W/E)
-                    const bool n_ = er == 0, s_ = er == TS - 1, w_ = ec == 0, e_ = ec == TS - 1;
-                    if (n_ | s_ | w_ | e_) {
-                        unsigned lists = 0;   // up to three list ids, 4 bits each
-                        int nl = 0;
-                        if (n_ | s_) { lists = s_ ? 1u : 0u; nl = 1; }
-                        if (w_ | e_) { lists |= (e_ ? 3u : 2u) << (4 * nl); ++nl; }
-                        if (nl == 2) { lists |= (4u + (s_ ? 2u : 0u) + (e_ ? 1u : 0u)) << 8; nl = 3; }
+                const bool n_ = er == 0, s_ = er == TS - 1, w_ = ec == 0, e_ = ec == TS - 1;
+                if (n_ | s_ | w_ | e_) {
+                    unsigned lists = 0;   // up to three list ids, 4 bits each
+                    int nl = 0;
+                    if (n_ | s_) { lists = s_ ? 1u : 0u; nl = 1; }
+                    if (w_ | e_) { lists |= (e_ ? 3u : 2u) << (4 * nl); ++nl; }
+                    if (nl == 2) { lists |= (4u + (s_ ? 2u : 0u) + (e_ ? 1u : 0u)) << 8; nl = 3; }
+                    double2* ohxy = reinterpret_cast<double2*>(row_ptr(P.exp_out, P.L, lr) + P.L.off_hxy) + (size_t)tc * D::HL;
 #pragma unroll 1
-                        for (int k = 0; k < nl; ++k) {
-                            const int list = (int)((lists >> (4 * k)) & 15u);
-                            const int idx = atomicAdd(&S.hout[list], 1);
-                            if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
-                        }
+                    for (int k = 0; k < nl; ++k) {
+                        const int list = (int)((lists >> (4 * k)) & 15u);
+                        const int idx = atomicAdd(&S.hout[list], 1);
+                        if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
                     }
-                } else {
-                    const int rank = -1 - dst[r];
-                    if (rank < CO) {
-                        OutRec rec;
-                        rec.x = q.x; rec.y = q.y; rec.vx = nv.x; rec.vy = nv.y;
-                        rec.ax = kStoreAcc ? nax[kStoreAcc ? r : 0] : 0.0;
-                        rec.ay = kStoreAcc ? nay[kStoreAcc ? r : 0] : 0.0;
-                        rec.id = st.id[i];
-                        rec.row = nrow; rec.col = ncol; rec.pad = 0;
-                        oobox[rank] = rec;
-                    }
-                    const int dtr = nrow / TS - tr, dtc = ncol / TS - tc;
-                    if (dtr < -1 || dtr > 1 || dtc < -1 || dtc > 1) tflags |= kErrLostParticle;
                 }
+            } else if (valid) {
+                const int rank = lbase + __popc(lm & lt_mask);
+                if (rank < CO) {
+                    OutRec* oobox = reinterpret_cast<OutRec*>(row_ptr(P.exp_out, P.L, lr) + P.L.off_obox) + (size_t)tc * CO;
+                    OutRec rec;
+                    rec.x = x; rec.y = y; rec.vx = v.x; rec.vy = v.y;
+                    rec.ax = kStoreAcc ? ax : 0.0;
+                    rec.ay = kStoreAcc ? ay : 0.0;
+                    rec.id = id;
+                    rec.row = nrow; rec.col = ncol; rec.pad = 0;
+                    oobox[rank] = rec;
+                }
+                // a particle may not skip a whole tile in one step
+                if ((unsigned)(nrow - r0 + TS) >= (unsigned)(3 * TS) || (unsigned)(ncol - c0 + TS) >= (unsigned)(3 * TS))
+                    atomicOr(&S.flags, kErrLostParticle);
             }
         }
-        // apron particles leave the cell table too; the occupancy map is small enough to clear whole
-        for (int q = tid; q < n_apron; q += T) {
-            const unsigned c = pcell[CAP + q];
-            if (c != 0xFFFFu) head[c] = kEmpty;
-        }
-        for (int c = tid; c < W * RW; c += T) rowbits[c] = 0u;
-        if (tflags) atomicOr(&S.flags, tflags);
-        if (tid == 0) {
-            const int stay_base = S.n_stay, leave_base = S.n_leave;   // tile totals
-            S.n_stay = S.n_leave = 0;
-            int* ecnt = reinterpret_cast<int*>(orow + P.L.off_cnt) + (size_t)tc * 16;
-            if (leave_base > CO) atomicOr(&S.flags, kErrOutboxOverflow);
-            ecnt[8] = min(leave_base, CO);
-            P.tcount[lt] = stay_base;
-            S.npairs = 0;
-            S.hw_leave = max(S.hw_leave, leave_base);
-            S.hw_tile = max(S.hw_tile, n_own);
-            S.hw_apron = max(S.hw_apron, n_apron);
-        }
-        fence_proxy_async();  // order this iteration's generic accesses to the stage before the next bulk copies
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[sb]);  // the producer may refill this stage once every consumer warp has arrived
-        prev_lr = lr;
-        prev_tc = tc;
         walk.advance(P);
+        PSIM_TICK(8);
+        PSIM_HIST(0, 2);
+        PSIM_HIST(1, 4);
+        PSIM_HIST(2, 8);
+        PSIM_HIST(3, 1);
     }
-    consumer_sync<T>();   // all halo-list appends of the last tile are done
-    if (prev_lr >= 0 && tid < 8) publish_halo_counts(prev_lr, prev_tc);
-    consumer_sync<T>();
+#ifdef PSIM_PHASE_TIMERS
+    if (lane == 0) for (int k = 0; k < 9; ++k) atomicAdd(&g_phase_cycles[warp][k], (unsigned long long)tacc[k]);
+#endif
+    named_sync<kBarPairs, T>();   // all appends and slot reservations of the last tile are done
+    if (tid < 9) publish_counts();
+    named_sync<kBarPairs, T>();
     if (tid == 0) {
         if (S.flags) atomicOr(P.err, S.flags);
         atomicMax(P.err + 1, S.hw_leave);
@@ -979,6 +1045,10 @@ static int configure(TiledEngine* e) {
     int per_sm = 0;
     PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_step_kernel<TS, false>, TileCfg<TS>::THREADS + 32, e->smem));
     e->ctas_per_sm = std::max(1, per_sm);
+    if (const char* cap = std::getenv("PSIM_CTAS_PER_SM")) {   // tuning / profiling knob
+        const int c = std::atoi(cap);
+        if (c >= 1) e->ctas_per_sm = std::min(e->ctas_per_sm, c);
+    }
     return PSIM_OK;
 }
 
@@ -1138,6 +1208,36 @@ int tiled_view(psim_sim* sim, SoAView* out) {
 void tiled_destroy(psim_sim* sim) {
     TiledEngine* e = sim->tiled;
     if (!e) return;
+#ifdef PSIM_PHASE_TIMERS
+    {
+        unsigned long long h[34][12];
+        cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof h);
+        const double tiles = (double)e->lrows * e->ntx * (double)std::max<long long>(sim->steps_done, 1);
+        const char* names[9] = {"top", "wait_full", "A", "bar1", "B", "bar2", "C", "bar3", "DE"};
+        const char* pnames[9] = {"top", "bar1", "issue", "bar2", "wait_full", "ingest", "-", "-", "-"};
+        for (int w = 0; w < 34; ++w) {
+            if (w == 33) for (int k = 0; k < 9; ++k) names[k] = pnames[k];
+            if (h[w][0] + h[w][2] == 0) continue;
+            std::fprintf(stderr, "[phase cycles/tile] %s%d:", w == 33 ? "producer" : "warp", w);
+            double tot = 0;
+            for (int k = 0; k < 9; ++k) {
+                std::fprintf(stderr, " %s=%.0f", names[k], h[w][k] / tiles);
+                tot += h[w][k] / tiles;
+            }
+            std::fprintf(stderr, " total=%.0f\n", tot);
+        }
+        unsigned hh[4][64];
+        cudaMemcpyFromSymbol(hh, g_hist, sizeof hh);
+        const char* hn[4] = {"A", "B", "DE", "wait_full"};
+        for (int a = 0; a < 4; ++a) {
+            std::fprintf(stderr, "[hist %s, 256-cycle bins]", hn[a]);
+            for (int b = 0; b < 64; ++b) if (hh[a][b]) std::fprintf(stderr, " %d:%u", b, hh[a][b]);
+            std::fprintf(stderr, "\n");
+        }
+        unsigned long long z[34][12] = {};
+        cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
+    }
+#endif
     e->gmem.release();
     e->mem.release();
     delete e;

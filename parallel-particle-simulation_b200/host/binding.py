@@ -61,7 +61,8 @@ class Info(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(BUILD, "libpsim.so")
+    # PSIM_LIB selects another build of the same library (e.g. the phase-timer profiling build)
+    return os.environ.get("PSIM_LIB") or os.path.join(BUILD, "libpsim.so")
 
 
 def build_native(force: bool = False) -> str:
