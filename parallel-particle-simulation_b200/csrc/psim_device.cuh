@@ -20,50 +20,29 @@ constexpr double kDt      = PSIM_DT;
 constexpr double kBin     = PSIM_BIN_SIZE;
 
 // Cell coordinate along one axis: floor(v / 0.01) with a correctly rounded IEEE division
-// (reference part1/serial.cpp:41-42; v*100.0 is NOT bit-identical).  Clamped to [0, bincnt-1]:
-// the reference indexes out of bounds for v == size when size/0.01 is an integer (e.g. 20 M
-// particles, size == 100.0); that state is unreachable in practice, the clamp only keeps memory safe.
-static __device__ __noinline__ int axis_cell_divide(double v) { return __double2int_rd(__ddiv_rn(v, kBin)); }
+// (reference part1/serial.cpp:41-42; v*100.0 is NOT bit-identical).
+//
+// div_by_bin(v) == RN(v / 0.01) bit for bit, without a division: q0 = RN(v * 100) is a faithful quotient
+// (0.01 is 2.1e-17 relative above 1/100, plus one rounding: < 0.7 ulp), r = v - q0 * 0.01 is exact in one FMA,
+// and 100.0 == RN(1 / 0.01), so RN(q0 + r * 100) is the correctly rounded quotient (Markstein's theorem).
+// oracle/check_div.c compares it with the hardware division on every double within 200 ulps of a cell edge
+// up to cell 40 000 and on 2e9 random positions: no mismatch (only the sign of a zero result differs).
+// Two FMAs instead of a ~20-instruction division with a slow-path call, and no data-dependent branch.
+__device__ __forceinline__ double div_by_bin(double v) {
+    const double q0 = __dmul_rn(v, 100.0);
+    const double r = __fma_rn(-q0, kBin, v);
+    return __fma_rn(r, 100.0, q0);
+}
 
-// Fast exact evaluation.  t = RN(v * 100) differs from the real quotient q = v / 0.01 by less than
-// |q| * 1.4e-16 (0.01 is 2.1e-17 relative above 1/100, plus one rounding), and so does RN(q).  Unless
-// t lies within 1e-9 of an integer, floor(t) == floor(RN(q)) for every |q| < 1e6 (error < 1.4e-10);
-// the rare values that close to a cell edge (and v == 0, -0) take the true division.
+// Clamped to [0, bincnt-1]: the reference indexes out of bounds for v == size when size/0.01 is an integer
+// (e.g. 20 M particles, size == 100.0); that state is unreachable in practice, the clamp only keeps memory safe.
 __device__ __forceinline__ int axis_cell(double v, int bincnt) {
-    const double t = __dmul_rn(v, 100.0);
-    int c = __double2int_rd(t);
-    const double f = __dsub_rn(t, __int2double_rn(c));
-    if (fabs(__dsub_rn(f, 0.5)) > 0.5 - 1e-9) c = axis_cell_divide(v);
-    return min(max(c, 0), bincnt - 1);
+    return min(max(__double2int_rd(div_by_bin(v)), 0), bincnt - 1);
 }
 
-// Both coordinates at once, one rare branch on the common path.  Also returns the unclamped floors (ix, iy)
-// of the products and their fractions (fx, fy), from which callers build an FP32 position in cell units.
-static __device__ __noinline__ int2 cell_of_exact(double x, double y, int bincnt) {
-    return make_int2(min(max(__double2int_rd(__ddiv_rn(x, kBin)), 0), bincnt - 1),
-                     min(max(__double2int_rd(__ddiv_rn(y, kBin)), 0), bincnt - 1));
-}
-__device__ __forceinline__ void cell_of_parts(double x, double y, int bincnt, int& row, int& col, int& ix, int& iy, double& fx,
-                                              double& fy) {
-    const double tx = __dmul_rn(x, 100.0), ty = __dmul_rn(y, 100.0);
-    ix = __double2int_rd(tx);
-    iy = __double2int_rd(ty);
-    fx = __dsub_rn(tx, __int2double_rn(ix));
-    fy = __dsub_rn(ty, __int2double_rn(iy));
-    row = ix;
-    col = iy;
-    // near a cell edge (or v == 0), or outside [0, bincnt): exact division and clamp
-    if (fmax(fabs(__dsub_rn(fx, 0.5)), fabs(__dsub_rn(fy, 0.5))) > 0.5 - 1e-9 || (unsigned)ix >= (unsigned)bincnt ||
-        (unsigned)iy >= (unsigned)bincnt) {
-        const int2 rc = cell_of_exact(x, y, bincnt);
-        row = rc.x;
-        col = rc.y;
-    }
-}
 __device__ __forceinline__ void cell_of(double x, double y, int bincnt, int& row, int& col) {
-    int ix, iy;
-    double fx, fy;
-    cell_of_parts(x, y, bincnt, row, col, ix, iy, fx, fy);
+    row = axis_cell(x, bincnt);
+    col = axis_cell(y, bincnt);
 }
 
 // Rank of a neighbour cell (dr, dc) in the reference's visiting order
@@ -88,13 +67,8 @@ __device__ __forceinline__ void pair_contrib(double dx, double dy, double r2, do
     cy = __dmul_rn(coef, dy);
 }
 
-// Integrate one particle and bounce it off the walls (reference part1/serial.cpp:46-61).
-__device__ __forceinline__ void move_particle(double& x, double& y, double& vx, double& vy, double ax, double ay,
-                                              double size) {
-    vx = __dadd_rn(vx, __dmul_rn(ax, kDt));
-    vy = __dadd_rn(vy, __dmul_rn(ay, kDt));
-    x = __dadd_rn(x, __dmul_rn(vx, kDt));
-    y = __dadd_rn(y, __dmul_rn(vy, kDt));
+// Bounce a particle off the walls (reference part1/serial.cpp:53-61).
+__device__ __forceinline__ void reflect_particle(double& x, double& y, double& vx, double& vy, double size) {
     if (x < 0 || x > size || y < 0 || y > size) {   // one rare branch on the common path
         const double two_size = __dmul_rn(2.0, size);
         while (x < 0 || x > size) {
@@ -106,6 +80,16 @@ __device__ __forceinline__ void move_particle(double& x, double& y, double& vx, 
             vy = -vy;
         }
     }
+}
+
+// Integrate one particle and bounce it off the walls (reference part1/serial.cpp:46-61).
+__device__ __forceinline__ void move_particle(double& x, double& y, double& vx, double& vy, double ax, double ay,
+                                              double size) {
+    vx = __dadd_rn(vx, __dmul_rn(ax, kDt));
+    vy = __dadd_rn(vy, __dmul_rn(ay, kDt));
+    x = __dadd_rn(x, __dmul_rn(vx, kDt));
+    y = __dadd_rn(y, __dmul_rn(vy, kDt));
+    reflect_particle(x, y, vx, vy, size);
 }
 
 // Canonical neighbour key: (visit rank of the neighbour's cell, neighbour x, neighbour y).

@@ -400,23 +400,21 @@ __device__ unsigned g_hist[4][64];   // histograms (256-cycle bins) of per-warp 
 // the per-step kernel
 // ------------------------------------------------------------------------------------------
 // Bin particle p of stage sb: exact cell, FP32 position in cell units relative to the table origin (cell
-// (r0-1, c0-1); integer part from the unclamped floor, fraction from the exact product: error < 4e-6 cells),
+// (r0-1, c0-1); rounding error < 4e-6 cells),
 // list head exchange, occupancy bit.  `ring_check`: apron entries may lie outside the table (never for the
 // lists of proper neighbours; kept as a memory-safety guard).
 template <int TS, bool kRingCheck>
 __device__ __forceinline__ void bin_particle(TileSmem<TS>& S, int sb, int p, double x, double y, int r0m1, int c0m1, int bincnt) {
     using D = TileDims<TS>;
-    int row, col, ix, iy;
-    double fx, fy;
-    cell_of_parts(x, y, bincnt, row, col, ix, iy, fx, fy);
-    const int lrow = row - r0m1, lcol = col - c0m1;
+    const double qx = div_by_bin(x), qy = div_by_bin(y);   // exact position in cell units
+    const int lrow = min(max(__double2int_rd(qx), 0), bincnt - 1) - r0m1, lcol = min(max(__double2int_rd(qy), 0), bincnt - 1) - c0m1;
     if (kRingCheck && ((unsigned)lrow >= (unsigned)D::W || (unsigned)lcol >= (unsigned)D::W)) return;
     const int cell = lrow * D::W + lcol;
     const unsigned old = atomicExch(&S.head[sb][cell], (unsigned)p);
     S.next[sb][p] = (unsigned short)old;
     S.pcell[p] = (unsigned short)cell;
     atomicOr(&S.rowbits[sb][lrow * D::RW + (lcol >> 5)], 1u << (lcol & 31));
-    S.rel[p] = make_float2(__int2float_rn(ix - r0m1) + __double2float_rn(fx), __int2float_rn(iy - c0m1) + __double2float_rn(fy));
+    S.rel[p] = make_float2(__double2float_rn(__dsub_rn(qx, (double)r0m1)), __double2float_rn(__dsub_rn(qy, (double)c0m1)));
 }
 
 template <int TS, bool kStoreAcc>
@@ -680,6 +678,21 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 if (!(r2 > kCutoff2) && r2 != 0.0) pair_contrib(dx, dy, r2, cx, cy);
                 S.pres[u] = make_double2(cx, cy);   // (+0, +0) for a prefilter false positive: neutral in the sum
             }
+            if (!kStoreAcc) {
+                // particles on the exact path (three or more candidates, or no room in the pair list): rare, and the
+                // only code with calls -- kept out of the move phase.  The acceleration is folded into the velocity
+                // right here (same two roundings as move_particle), the move phase then skips that update.
+#pragma unroll 1
+                for (int i = tid; i < n_own; i += T) {
+                    if (S.pcode[i] != 3u) continue;
+                    const double2 a = slow_force<W>(st.xy, head, next, i, S.pcell[i]);
+                    double2 v = st.v[i];
+                    v.x = __dadd_rn(v.x, __dmul_rn(a.x, kDt));
+                    v.y = __dadd_rn(v.y, __dmul_rn(a.y, kDt));
+                    st.v[i] = v;
+                    S.pcode[i] = 4u;   // velocity already advanced
+                }
+            }
             unsigned* oh = S.head[sb ^ 1];
             unsigned* ob = S.rowbits[sb ^ 1];
 #pragma unroll 1
@@ -714,7 +727,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 id = st.id[i];
                 x = p.x;
                 y = p.y;
-                if (fc == 3u) {
+                if (kStoreAcc && fc == 3u) {
                     // (the cell is recomputed: pcell may already hold the next tile's entries)
                     int srow, scol;
                     cell_of(x, y, P.bincnt, srow, scol);
@@ -722,15 +735,21 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                     ax = a.x;
                     ay = a.y;
                 } else if (fc != 0u) {
-                    const double2 c0_ = S.pres[code >> 2];
+                    const double2 c0_ = S.pres[(code >> 2) & 0x3FFFu];
                     ax = __dadd_rn(ax, c0_.x);
                     ay = __dadd_rn(ay, c0_.y);
                     if (fc == 2u) {
-                        const double2 c1_ = S.pres[(code >> 2) + 1];
+                        const double2 c1_ = S.pres[((code >> 2) & 0x3FFFu) + 1];
                         ax = __dadd_rn(ax, c1_.x);
                         ay = __dadd_rn(ay, c1_.y);
                     }
                 }
+                if (!kStoreAcc && code == 4u) {
+                    // exact-path particle: v already holds v + a dt
+                    x = __dadd_rn(x, __dmul_rn(v.x, kDt));
+                    y = __dadd_rn(y, __dmul_rn(v.y, kDt));
+                    reflect_particle(x, y, v.x, v.y, P.size);
+                } else
                 move_particle(x, y, v.x, v.y, ax, ay, P.size);
                 cell_of(x, y, P.bincnt, nrow, ncol);
                 stay = (unsigned)(nrow - r0) < (unsigned)TS && (unsigned)(ncol - c0) < (unsigned)TS;
