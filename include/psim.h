@@ -98,6 +98,7 @@ typedef struct psim_info_t {
      * fixed capacities (outbox records per tile-step, edge halo list length, tile population, apron) */
     int hw_leavers, hw_halo_list, hw_tile_population, hw_apron;
     int outbox_capacity, halo_list_capacity;
+    int reserved_hw_pairs;  /* tiled engine: most candidate pairs one tile listed in a step (capacity is internal) */
 } psim_info_t;
 
 /* ---- errors ---- */

@@ -198,6 +198,7 @@ static int check_device_error(psim_sim* sim) {
     PSIM_CUDA(cudaMemcpyAsync(sim->h_err, sim->d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
     PSIM_CUDA(cudaStreamSynchronize(sim->stream));
     const int e = *sim->h_err;
+    if (sim->h_err[5]) return fail(PSIM_ERR_STATE, "debug guard 0x%x tripped (last tile %d, flags 0x%x)", sim->h_err[5], sim->h_err[6], e);
     if (e == 0) return PSIM_OK;
     return fail(PSIM_ERR_CAPACITY,
                 "device capacity error 0x%x:%s%s%s%s%s (high-water marks: leavers/tile-step %d, edge halo list %d, tile population "
@@ -588,6 +589,7 @@ int psim_info(psim_sim* sim, psim_info_t* out) {
         out->hw_halo_list = sim->h_err[2];
         out->hw_tile_population = sim->h_err[3];
         out->hw_apron = sim->h_err[4];
+        out->reserved_hw_pairs = sim->h_err[7];
     }
     return PSIM_OK;
 }

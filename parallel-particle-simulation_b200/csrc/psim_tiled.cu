@@ -117,7 +117,7 @@ template <int TS> struct __align__(16) TileSmem {
     int prev_lr, prev_tc;                     // tile whose export counts still have to be published
     int npairs, flags;
     int n_stay, n_leave;                      // stayers / leavers of the current tile (warp-aggregated atomics)
-    int hw_leave, hw_halo, hw_tile, hw_apron;   // high-water marks over the tiles this CTA processed
+    int hw_leave, hw_halo, hw_tile, hw_apron, hw_pairs;   // high-water marks over the tiles this CTA processed
 };
 
 static_assert(4 * (sizeof(TileSmem<32>) + 1024) <= 233472, "four CTAs of the 32-cell tile kernel must fit one SM's shared memory");
@@ -378,6 +378,18 @@ static __device__ __noinline__ double2 slow_force(const double2* xy, const unsig
     return make_double2(ax, ay);
 }
 
+#ifdef PSIM_DEBUG_GUARDS
+// debug build only: bounds guards on every data-dependent shared-memory index; a hit sets a bit in err[5]
+#define PSIM_GUARD(cond, bit, ...)                 \
+    if (!(cond)) {                                 \
+        atomicOr(P.err + 5, 1 << (bit));           \
+        atomicMax(P.err + 6, first + it * G);      \
+        __VA_ARGS__;                               \
+    }
+#else
+#define PSIM_GUARD(cond, bit, ...)
+#endif
+
 #ifdef PSIM_PHASE_TIMERS
 // profiling build only: cycles spent per phase, summed over tiles, for warp 0, a middle warp and the loader warp
 __device__ unsigned long long g_phase_cycles[34][12];
@@ -408,6 +420,9 @@ __device__ __forceinline__ void bin_particle(TileSmem<TS>& S, int sb, int p, dou
     using D = TileDims<TS>;
     const double qx = div_by_bin(x), qy = div_by_bin(y);   // exact position in cell units
     const int lrow = min(max(__double2int_rd(qx), 0), bincnt - 1) - r0m1, lcol = min(max(__double2int_rd(qy), 0), bincnt - 1) - c0m1;
+#ifdef PSIM_DEBUG_GUARDS
+    if ((unsigned)lrow >= (unsigned)D::W || (unsigned)lcol >= (unsigned)D::W || (unsigned)p >= (unsigned)D::PTOT) { atomicOr(&S.flags, 1 << 20); return; }
+#endif
     if (kRingCheck && ((unsigned)lrow >= (unsigned)D::W || (unsigned)lcol >= (unsigned)D::W)) return;
     const int cell = lrow * D::W + lcol;
     const unsigned old = atomicExch(&S.head[sb][cell], (unsigned)p);
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         S.npairs = 0;
         S.flags = 0;
         S.n_stay = S.n_leave = 0;
-        S.hw_leave = S.hw_halo = S.hw_tile = S.hw_apron = 0;
+        S.hw_leave = S.hw_halo = S.hw_tile = S.hw_apron = S.hw_pairs = 0;
         S.prev_lr = -1;
         S.prev_tc = 0;
     }
@@ -618,6 +633,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         for (int i = tid; i < n_own; i += T) {
             const int cell = S.pcell[i];
             const int lrow = cell / W, lcol = cell - lrow * W;
+            PSIM_GUARD(lrow >= 1 && lrow <= TS && lcol >= 1 && lcol <= TS, 0, continue)
             const float2 ri = S.rel[i];
             // 9 occupancy bits of the 3x3 neighbourhood, bit 3*(dr+1) + (dc+1)
             const unsigned* rb = S.rowbits[sb] + (lrow - 1) * RW + ((lcol - 1) >> 5);
@@ -634,6 +650,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 const int q = (k * 11) >> 5;   // k / 3
                 unsigned h = head[cell + q * (W - 3) + k - (W + 1)];
                 do {   // the occupancy bit guarantees a non-empty list
+                    PSIM_GUARD(h < (unsigned)D::PTOT, 1, break)
                     const float2 rj = S.rel[h];
                     const unsigned hn = next[h];
                     const float dx = rj.x - ri.x, dy = rj.y - ri.y;
@@ -656,6 +673,9 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                     if (fc == 2) S.pij[base + 1] = (unsigned)i | (cand & 0xFFFF0000u);
                     code = (unsigned)fc | ((unsigned)base << 2);
                 } else {
+                    // no room: exact path.  The reserved entry below NP (at most one) must still be well formed
+                    // for the evaluation loop: a self pair (distance 0) contributes nothing.
+                    if (base < NP) S.pij[base] = (unsigned)i | ((unsigned)i << 16);
                     code = 3;
                 }
             }
@@ -671,6 +691,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             const int np = min(S.npairs, NP);
             for (int u = T - 1 - tid; u < np; u += T) {
                 const unsigned ij = S.pij[u];
+                PSIM_GUARD((ij & 0xFFFFu) < (unsigned)D::PTOT && (ij >> 16) < (unsigned)D::PTOT, 2, continue)
                 const double2 a = st.xy[ij & 0xFFFFu], b = st.xy[ij >> 16];
                 const double dx = __dsub_rn(b.x, a.x), dy = __dsub_rn(b.y, a.y);
                 const double r2 = pair_r2(dx, dy);
@@ -704,6 +725,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         named_sync<kBarForces, T + 32>();   // (3) contributions ready, other table clean
         PSIM_TICK(7);
         if (tid == 0) {
+            S.hw_pairs = max(S.hw_pairs, S.npairs);
             S.npairs = 0;   // next appended to after barrier 1 of the next tile
             S.prev_lr = lr;
             S.prev_tc = tc;
@@ -722,6 +744,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             bool stay = false;
             if (valid) {
                 const unsigned code = S.pcode[i], fc = code & 3u;
+                PSIM_GUARD(code == 4u || (fc == 3u ? code == 3u : (fc == 0u ? code == 0u : ((code >> 2) + fc) <= (unsigned)NP)), 3)
                 const double2 p = st.xy[i];
                 v = st.v[i];
                 id = st.id[i];
@@ -763,6 +786,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             }
             sbase = __shfl_sync(0xffffffffu, sbase, 0);
             if (lm) lbase = __shfl_sync(0xffffffffu, lbase, 0);
+            PSIM_GUARD(!stay || (unsigned)(sbase + __popc(sm & lt_mask)) < (unsigned)CAP, 4, stay = false)
             if (stay) {
                 const double2 q = make_double2(x, y);
                 const size_t d = gbase + (size_t)(sbase + __popc(sm & lt_mask));
@@ -824,6 +848,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         atomicMax(P.err + 2, S.hw_halo);
         atomicMax(P.err + 3, S.hw_tile);
         atomicMax(P.err + 4, S.hw_apron);
+        atomicMax(P.err + 7, S.hw_pairs);
     }
 }
 

@@ -57,7 +57,7 @@ class Info(C.Structure):
                 ("nranks", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("steps_done", C.c_longlong),
                 ("kernel_launches", C.c_longlong), ("device_bytes", C.c_longlong), ("hw_leavers", C.c_int),
                 ("hw_halo_list", C.c_int), ("hw_tile_population", C.c_int), ("hw_apron", C.c_int),
-                ("outbox_capacity", C.c_int), ("halo_list_capacity", C.c_int)]
+                ("outbox_capacity", C.c_int), ("halo_list_capacity", C.c_int), ("reserved_hw_pairs", C.c_int)]
 
 
 def lib_path() -> str:

@@ -180,6 +180,31 @@ def test_edge_cases(pkg, oracle, engine):
         sim.close()
 
 
+@pytest.mark.parametrize("engine", ["cellsort", "tiled16", "tiled32"])
+def test_pair_list_overflow_takes_the_exact_path(pkg, oracle, engine):
+    """More candidate pairs inside one tile than the tiled engine's shared-memory pair list holds (32 entries for
+    16-cell tiles, 64 for 32-cell tiles): a serpentine chain, every particle with two neighbours at 0.8 cutoff.
+    The overflow must fall back to the exact path and stay bit-identical to the oracle."""
+    size = box_size(4000)
+    pts = []
+    for r in range(6):                       # 6 rows, 0.012 apart (rows do not interact), 14 particles each, 0.008 apart
+        xs = 0.205 + 0.008 * np.arange(14)
+        pts += [(x if r % 2 == 0 else xs[-1] - (x - xs[0]), 0.21 + 0.012 * r) for x in xs]
+    parts = np.zeros((len(pts), 6))
+    parts[:, :2] = np.array(pts)
+    parts[:, 2] = 0.01 * np.cos(np.arange(len(pts)))
+    want = parts.copy()
+    sim = make_sim(pkg, parts, size, engine)
+    for _ in range(4):
+        oracle.step(want, size, 1)
+        got = sim.step(1).sync().read_particles()
+        assert np.array_equal(got, want)
+    assert np.abs(want[:, 4:]).max() > 0
+    if engine != "cellsort":
+        assert sim.info()["reserved_hw_pairs"] > (32 if engine == "tiled16" else 64)
+    sim.close()
+
+
 def test_empty_and_dense_inputs(pkg, oracle):
     sim = pkg.Simulation(np.zeros((0, 6)), 0, 0.5)
     sim.step(3).sync()
