@@ -87,6 +87,11 @@ int tiled_exchange(psim_sim* sim, int parity, cudaStream_t s) {
 void comm_destroy(psim_sim* sim) {
     if (sim->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(sim->comm));
     sim->comm = nullptr;
+    if (sim->ev_boundary) cudaEventDestroy(sim->ev_boundary);
+    if (sim->ev_exchanged) cudaEventDestroy(sim->ev_exchanged);
+    if (sim->comm_stream) cudaStreamDestroy(sim->comm_stream);
+    sim->ev_boundary = sim->ev_exchanged = nullptr;
+    sim->comm_stream = nullptr;
 }
 
 }  // namespace psim
@@ -114,5 +119,10 @@ extern "C" int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]) 
     ncclComm_t comm = nullptr;
     PSIM_NCCL(g_nccl.CommInitRank(&comm, sim->nranks, id, sim->rank));
     sim->comm = comm;
+    int lo = 0, hi = 0;
+    PSIM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PSIM_CUDA(cudaStreamCreateWithPriority(&sim->comm_stream, cudaStreamNonBlocking, hi));   // exchange first
+    PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_boundary, cudaEventDisableTiming));
+    PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_exchanged, cudaEventDisableTiming));
     return PSIM_OK;
 }

@@ -115,6 +115,10 @@ struct psim_sim {
     // scratch for observation calls
     psim::DeviceArena scratch;
     void* comm = nullptr;  // ncclComm_t when connected
+    // slab exchange runs on its own stream so that it overlaps the interior tile rows of the same step
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_boundary = nullptr;   // boundary tile rows of the current step are done (compute stream)
+    cudaEvent_t ev_exchanged = nullptr;  // ghost rows hold the neighbours' exports (comm stream)
 };
 
 namespace psim {

@@ -137,6 +137,7 @@ struct TileParams {
     int ntx, nty;    // tiles per side (global)
     int tr_base;     // global tile row of local row 0
     int lrow0;       // first local tile row of this launch
+    int row_stride;  // tile t of the launch lies in local row lrow0 + (t / ntx) * row_stride (boundary launch: first and last row)
     int ntiles;      // tiles of this launch (rows * ntx)
     int bincnt;
     double size;
@@ -223,7 +224,7 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord tile_coord(const TileParams& P, int t) {
     TileCoord c;
-    c.lr = P.lrow0 + t / P.ntx;
+    c.lr = P.lrow0 + (t / P.ntx) * P.row_stride;
     c.tc = t % P.ntx;
     c.tr = P.tr_base + c.lr;
     c.lt = c.lr * P.ntx + c.tc;
@@ -234,9 +235,9 @@ __device__ __forceinline__ TileCoord tile_coord(const TileParams& P, int t) {
 struct TileWalker {
     int lr, tc, gq, gr;
     __device__ __forceinline__ void init(const TileParams& P, int first, int G) {
-        lr = P.lrow0 + first / P.ntx;
+        lr = P.lrow0 + (first / P.ntx) * P.row_stride;
         tc = first % P.ntx;
-        gq = G / P.ntx;
+        gq = (G / P.ntx) * P.row_stride;
         gr = G % P.ntx;
     }
     __device__ __forceinline__ void advance(const TileParams& P) {
@@ -244,7 +245,7 @@ struct TileWalker {
         lr += gq;
         if (tc >= P.ntx) {
             tc -= P.ntx;
-            ++lr;
+            lr += P.row_stride;
         }
     }
     __device__ __forceinline__ TileCoord coord(const TileParams& P) const {
@@ -1042,6 +1043,7 @@ static TileParams make_params(psim_sim* sim, TiledEngine* e, int parity_in) {
     P.nty = e->ntx;
     P.tr_base = e->tr_begin - 1;
     P.lrow0 = 1;
+    P.row_stride = 1;
     P.ntiles = e->lrows * e->ntx;
     P.bincnt = sim->bincnt;
     P.size = sim->size;
@@ -1050,10 +1052,12 @@ static TileParams make_params(psim_sim* sim, TiledEngine* e, int parity_in) {
 }
 
 template <int TS>
-static int launch_step(psim_sim* sim, TiledEngine* e, int parity_in, bool store_acc, int lrow0, int nrows, cudaStream_t s) {
+static int launch_step(psim_sim* sim, TiledEngine* e, int parity_in, bool store_acc, int lrow0, int nrows, int row_stride,
+                       cudaStream_t s) {
     if (nrows <= 0) return PSIM_OK;
     TileParams P = make_params(sim, e, parity_in);
     P.lrow0 = lrow0;
+    P.row_stride = row_stride;
     P.ntiles = nrows * e->ntx;
     const int grid = std::min(P.ntiles, e->sms * e->ctas_per_sm);
     if (store_acc)
@@ -1064,11 +1068,12 @@ static int launch_step(psim_sim* sim, TiledEngine* e, int parity_in, bool store_
     return PSIM_OK;
 }
 
-static int launch_step_ts(psim_sim* sim, TiledEngine* e, int parity_in, bool store_acc, int lrow0, int nrows, cudaStream_t s) {
+static int launch_step_ts(psim_sim* sim, TiledEngine* e, int parity_in, bool store_acc, int lrow0, int nrows, cudaStream_t s,
+                          int row_stride = 1) {
     switch (e->ts) {
-        case 16: return launch_step<16>(sim, e, parity_in, store_acc, lrow0, nrows, s);
-        case 32: return launch_step<32>(sim, e, parity_in, store_acc, lrow0, nrows, s);
-        case 64: return launch_step<64>(sim, e, parity_in, store_acc, lrow0, nrows, s);
+        case 16: return launch_step<16>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, s);
+        case 32: return launch_step<32>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, s);
+        case 64: return launch_step<64>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, s);
     }
     return fail(PSIM_ERR_INVALID, "tile size %d not instantiated", e->ts);
 }
@@ -1198,15 +1203,30 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
 int tiled_step(psim_sim* sim, int nsteps, int flags) {
     TiledEngine* e = sim->tiled;
     cudaStream_t s = sim->stream;
+    const bool slabs = sim->nranks > 1;
+    if (slabs && !sim->comm) return fail(PSIM_ERR_STATE, "slab %d/%d is not connected: call psim_comm_connect first", sim->rank, sim->nranks);
     for (int step = 0; step < nsteps; ++step) {
         const bool store = (flags & PSIM_STEP_ACCEL_ALL) || (!(flags & PSIM_STEP_ACCEL_NONE) && step == nsteps - 1);
-        if (sim->nranks > 1 && !e->ghost_fresh) {
-            PSIM_TRY(tiled_exchange(sim, e->parity, s));
-            e->ghost_fresh = true;
+        if (!slabs) {
+            PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, e->lrows, s));
+        } else {
+            // Slab step: the first and last owned tile rows go first; as soon as they are done
+            // their exports (halo lists + migrants) travel to the neighbours on the exchange stream while the
+            // interior rows are computed.  The next step's boundary rows wait for both.
+            if (!e->ghost_fresh) {   // first step after create: the neighbours' initial exports
+                PSIM_TRY(tiled_exchange(sim, e->parity, s));
+                e->ghost_fresh = true;
+            }
+            if (e->lrows <= 2) PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, e->lrows, s));
+            else PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, 2, s, e->lrows - 1));   // rows 1 and lrows in one launch
+            PSIM_CUDA(cudaEventRecord(sim->ev_boundary, s));
+            PSIM_CUDA(cudaStreamWaitEvent(sim->comm_stream, sim->ev_boundary, 0));
+            PSIM_TRY(tiled_exchange(sim, e->parity ^ 1, sim->comm_stream));
+            PSIM_CUDA(cudaEventRecord(sim->ev_exchanged, sim->comm_stream));
+            if (e->lrows > 2) PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 2, e->lrows - 2, s));
+            PSIM_CUDA(cudaStreamWaitEvent(s, sim->ev_exchanged, 0));   // the next step (or an observation) sees fresh ghost rows
         }
-        PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, e->lrows, s));
         e->parity ^= 1;
-        if (sim->nranks > 1) PSIM_TRY(tiled_exchange(sim, e->parity, s));
         e->acc_valid = store;
         ++sim->steps_done;
     }

@@ -247,6 +247,23 @@ def test_device_pointer_flavour(pkg, oracle):
     sim.close()
 
 
+# ---------------------------------------------------------------- slabs over several GPUs
+@pytest.mark.parametrize("tile", [16, 32])
+def test_slabs_match_oracle_on_all_visible_gpus(tile):
+    """One process per GPU (torchrun), halo exchange + migration over NCCL, merged state bit-identical to the oracle."""
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    world = min(ngpu, 8)
+    n = 60000 if tile == 16 else 400000
+    cmd = ["python", "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + tile), os.path.join(os.path.dirname(__file__), "slab_check.py"), str(n), "120", str(tile)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "SLAB_CHECK ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 # ---------------------------------------------------------------- drop-in drivers (SURVEY 8b)
 def _trajectory_md5(cmd, tmp_path, env=None):
     out = tmp_path / "traj.txt"
