@@ -8,11 +8,13 @@
 //
 // NCCL is bound at run time (dlopen) so that libpsim has no link-time dependency on a particular
 // NCCL build: inside a torch process `libnccl.so.2` resolves to the copy torch already loaded.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "psim_internal.h"
 
@@ -66,6 +68,8 @@ static int load_nccl() {
 
 int tiled_exchange(psim_sim* sim, int parity, cudaStream_t s) {
     if (sim->nranks == 1) return PSIM_OK;
+    static const bool skip = std::getenv("PSIM_DEBUG_SKIP_EXCHANGE") != nullptr;   // timing experiments only: results are wrong
+    if (skip) return PSIM_OK;
     if (!sim->comm) return fail(PSIM_ERR_STATE, "slab %d/%d is not connected: call psim_comm_connect first", sim->rank, sim->nranks);
     ncclComm_t comm = static_cast<ncclComm_t>(sim->comm);
     char *first, *last, *glo, *ghi;
@@ -84,7 +88,127 @@ int tiled_exchange(psim_sim* sim, int parity, cudaStream_t s) {
     return PSIM_OK;
 }
 
+// ---- peer-memory exchange ----------------------------------------------------------------------------
+// Each slab maps its neighbours' export buffers and flag words (CUDA IPC; the 64-byte handles travel through the
+// NCCL communicator once at connect time).  Per step: the kernel stores its boundary rows' exports into the
+// neighbours' ghost rows, a one-thread kernel then writes my step count into their flag words, and my next step
+// is ordered behind THEIR flags with cuStreamWaitValue32 (no SM, no host round trip).
+struct P2PHandles {
+    cudaIpcMemHandle_t exports[2];
+    cudaIpcMemHandle_t flags;
+};
+
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WaitValue32Fn g_wait_value32 = nullptr;
+
+static int p2p_setup(psim_sim* sim, ncclComm_t comm) {
+    const char* env = std::getenv("PSIM_P2P");
+    if (env && env[0] == '0') return PSIM_OK;
+    char *e0, *e1;
+    size_t bytes, row_bytes;
+    int lrows, ntx;
+    tiled_export_buffers(sim, &e0, &e1, &bytes, &row_bytes, &lrows, &ntx);
+    if (ntx / sim->nranks < 2) return PSIM_OK;   // (same decision on every rank) a one-row slab would have to mirror the same row to both sides: keep NCCL
+    (void)lrows;
+    if (!g_wait_value32) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return PSIM_OK;   // no stream memory operations: keep NCCL
+        }
+        g_wait_value32 = reinterpret_cast<WaitValue32Fn>(fn);
+    }
+    PSIM_CUDA(cudaMalloc(&sim->d_flags, 2 * sizeof(int)));
+    PSIM_CUDA(cudaMemset(sim->d_flags, 0, 2 * sizeof(int)));
+    P2PHandles mine{}, theirs[2]{};
+    PSIM_CUDA(cudaIpcGetMemHandle(&mine.exports[0], e0));
+    PSIM_CUDA(cudaIpcGetMemHandle(&mine.exports[1], e1));
+    PSIM_CUDA(cudaIpcGetMemHandle(&mine.flags, sim->d_flags));
+    // swap handles with the neighbours (through device buffers: NCCL moves device memory)
+    P2PHandles* d_buf = nullptr;   // [0] mine, [1] from below, [2] from above
+    PSIM_CUDA(cudaMalloc(&d_buf, 3 * sizeof(P2PHandles)));
+    PSIM_CUDA(cudaMemcpy(d_buf, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    cudaStream_t s = sim->comm_stream;
+    PSIM_NCCL(g_nccl.GroupStart());
+    if (sim->rank > 0) {
+        PSIM_NCCL(g_nccl.Send(d_buf, sizeof(P2PHandles), ncclInt8, sim->rank - 1, comm, s));
+        PSIM_NCCL(g_nccl.Recv(d_buf + 1, sizeof(P2PHandles), ncclInt8, sim->rank - 1, comm, s));
+    }
+    if (sim->rank < sim->nranks - 1) {
+        PSIM_NCCL(g_nccl.Send(d_buf, sizeof(P2PHandles), ncclInt8, sim->rank + 1, comm, s));
+        PSIM_NCCL(g_nccl.Recv(d_buf + 2, sizeof(P2PHandles), ncclInt8, sim->rank + 1, comm, s));
+    }
+    PSIM_NCCL(g_nccl.GroupEnd());
+    PSIM_CUDA(cudaStreamSynchronize(s));
+    PSIM_CUDA(cudaMemcpy(theirs, d_buf + 1, 2 * sizeof(P2PHandles), cudaMemcpyDeviceToHost));
+    cudaFree(d_buf);
+    for (int side = 0; side < 2; ++side) {
+        const bool have = side == 0 ? sim->rank > 0 : sim->rank < sim->nranks - 1;
+        if (!have) continue;
+        for (int b = 0; b < 2; ++b) {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, theirs[side].exports[b], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(PSIM_ERR_COMM, "cudaIpcOpenMemHandle(neighbour exports): %s", cudaGetErrorString(e));
+            sim->peer_exports[side][b] = static_cast<char*>(p);
+        }
+        void* f = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&f, theirs[side].flags, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(PSIM_ERR_COMM, "cudaIpcOpenMemHandle(neighbour flags): %s", cudaGetErrorString(e));
+        sim->peer_flags[side] = static_cast<int*>(f);
+    }
+    sim->p2p = true;
+    sim->p2p_steps = 0;
+    return PSIM_OK;
+}
+
+int comm_p2p_wait(psim_sim* sim, cudaStream_t s) {
+    if (!sim->p2p || sim->p2p_steps == 0) return PSIM_OK;
+    for (int side = 0; side < 2; ++side) {
+        const bool have = side == 0 ? sim->rank > 0 : sim->rank < sim->nranks - 1;
+        if (!have) continue;
+        const CUresult r = g_wait_value32(reinterpret_cast<CUstream>(s), reinterpret_cast<CUdeviceptr>(sim->d_flags + side),
+                                          sim->p2p_steps, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) return fail(PSIM_ERR_COMM, "cuStreamWaitValue32 failed (%d)", (int)r);
+    }
+    return PSIM_OK;
+}
+
+int comm_p2p_signal(psim_sim* sim, cudaStream_t s) {
+    if (!sim->p2p) return PSIM_OK;
+    ++sim->p2p_steps;
+    // my lower neighbour sees me as ITS upper neighbour (flag word 1) and vice versa
+    launch_flag_store(sim->peer_flags[0] ? sim->peer_flags[0] + 1 : nullptr, sim->peer_flags[1] ? sim->peer_flags[1] + 0 : nullptr,
+                      (int)sim->p2p_steps, s);
+    PSIM_CUDA(cudaGetLastError());
+    return PSIM_OK;
+}
+
 void comm_destroy(psim_sim* sim) {
+    if (sim->p2p && sim->d_flags) {
+        // the neighbours store into my ghost rows until they have finished the same step: do not unmap / free before
+        // (host-side poll with a time-out: a neighbour that ran fewer steps must not hang this process for ever)
+        cudaStreamSynchronize(sim->stream);
+        for (int spin = 0; spin < 20000; ++spin) {
+            int f[2] = {0, 0};
+            if (cudaMemcpy(f, sim->d_flags, sizeof f, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+            const bool lo_ok = sim->rank == 0 || (unsigned)f[0] >= sim->p2p_steps;
+            const bool hi_ok = sim->rank == sim->nranks - 1 || (unsigned)f[1] >= sim->p2p_steps;
+            if (lo_ok && hi_ok) break;
+            struct timespec ts = {0, 500000};
+            nanosleep(&ts, nullptr);
+        }
+    }
+    for (int side = 0; side < 2; ++side) {
+        for (int b = 0; b < 2; ++b)
+            if (sim->peer_exports[side][b]) cudaIpcCloseMemHandle(sim->peer_exports[side][b]);
+        if (sim->peer_flags[side]) cudaIpcCloseMemHandle(sim->peer_flags[side]);
+        sim->peer_exports[side][0] = sim->peer_exports[side][1] = nullptr;
+        sim->peer_flags[side] = nullptr;
+    }
+    if (sim->d_flags) cudaFree(sim->d_flags);
+    sim->d_flags = nullptr;
+    sim->p2p = false;
     if (sim->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(sim->comm));
     sim->comm = nullptr;
     if (sim->ev_boundary) cudaEventDestroy(sim->ev_boundary);
@@ -124,5 +248,6 @@ extern "C" int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]) 
     PSIM_CUDA(cudaStreamCreateWithPriority(&sim->comm_stream, cudaStreamNonBlocking, hi));   // exchange first
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_boundary, cudaEventDisableTiming));
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_exchanged, cudaEventDisableTiming));
+    if (sim->tiled) PSIM_TRY(p2p_setup(sim, comm));
     return PSIM_OK;
 }

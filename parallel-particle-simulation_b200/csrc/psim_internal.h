@@ -119,6 +119,13 @@ struct psim_sim {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_boundary = nullptr;   // boundary tile rows of the current step are done (compute stream)
     cudaEvent_t ev_exchanged = nullptr;  // ghost rows hold the neighbours' exports (comm stream)
+    // peer-memory exchange (default for slabs on one NVSwitch box): the step kernel stores the exports of its boundary
+    // tile rows straight into the neighbour's ghost rows; a flag per neighbour orders the steps
+    bool p2p = false;
+    int* d_flags = nullptr;                 // [0] written by the lower neighbour, [1] by the upper: its completed step count
+    char* peer_exports[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][parity]: neighbour's export buffers, mapped
+    int* peer_flags[2] = {nullptr, nullptr};                               // [side]: neighbour's d_flags, mapped
+    unsigned p2p_steps = 0;                 // steps signalled so far
 };
 
 namespace psim {
@@ -136,6 +143,10 @@ int tiled_exchange(psim_sim* sim, int parity, cudaStream_t s);  // psim_comm.cpp
 void tiled_boundary_rows(psim_sim* sim, int parity, char** first_owned, char** last_owned, char** ghost_lo, char** ghost_hi,
                          size_t* row_bytes);
 void comm_destroy(psim_sim* sim);
+int comm_p2p_wait(psim_sim* sim, cudaStream_t s);     // stream waits until both neighbours have finished step p2p_steps
+int comm_p2p_signal(psim_sim* sim, cudaStream_t s);   // tell both neighbours that my step ++p2p_steps is finished
+void tiled_export_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, size_t* row_bytes, int* lrows, int* ntx);
+void launch_flag_store(int* flag_a, int* flag_b, int value, cudaStream_t s);   // psim_tiled.cu
 int tiled_step(psim_sim* sim, int nsteps, int flags);
 int tiled_view(psim_sim* sim, SoAView* out);  // gathers into scratch
 void tiled_destroy(psim_sim* sim);

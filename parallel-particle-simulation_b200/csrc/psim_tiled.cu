@@ -142,6 +142,10 @@ struct TileParams {
     int bincnt;
     double size;
     int* err;
+    // slabs with peer-memory exchange: the exports of the first / last owned tile row are ALSO written straight into
+    // the neighbour GPU's ghost row (NVLink peer stores), so the step needs no separate exchange
+    char* peer_row[2];   // [0] lower neighbour's upper ghost row, [1] upper neighbour's lower ghost row (parity written); or null
+    int last_lrow;       // local index of the last owned tile row
 };
 
 __device__ __forceinline__ const char* row_ptr(const char* base, const ExportLayout& L, int lrow) {
@@ -149,6 +153,10 @@ __device__ __forceinline__ const char* row_ptr(const char* base, const ExportLay
 }
 __device__ __forceinline__ char* row_ptr(char* base, const ExportLayout& L, int lrow) {
     return base + (size_t)lrow * L.row_bytes;
+}
+// the neighbour's ghost row that mirrors local row lr (null for interior rows and without peer exchange)
+__device__ __forceinline__ char* peer_row_of(const TileParams& P, int lr) {
+    return lr == 1 ? P.peer_row[0] : (lr == P.last_lrow ? P.peer_row[1] : nullptr);
 }
 
 // Apron source k = 0..7: which neighbour (dr, dc) and which of ITS lists faces this tile.
@@ -433,7 +441,7 @@ __device__ __forceinline__ void bin_particle(TileSmem<TS>& S, int sb, int p, dou
     S.rel[p] = make_float2(__double2float_rn(__dsub_rn(qx, (double)r0m1)), __double2float_rn(__dsub_rn(qy, (double)c0m1)));
 }
 
-template <int TS, bool kStoreAcc>
+template <int TS, bool kStoreAcc, bool kPeer>
 __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) tile_step_kernel(const TileParams P) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
@@ -578,10 +586,13 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         const int done_lr = S.prev_lr, done_tc = S.prev_tc;
         if (done_lr < 0) return;
         int* ec = reinterpret_cast<int*>(row_ptr(P.exp_out, P.L, done_lr) + P.L.off_cnt) + (size_t)done_tc * 16;
+        char* prow = kPeer ? peer_row_of(P, done_lr) : nullptr;
+        int* pec = prow ? reinterpret_cast<int*>(prow + P.L.off_cnt) + (size_t)done_tc * 16 : nullptr;
         if (tid < 8) {
             const int k = S.hout[tid], cap = halo_cap(tid, HE, HC);
             if (k > cap) atomicOr(&S.flags, kErrHaloOverflow);
             ec[tid] = min(k, cap);
+            if (pec) pec[tid] = min(k, cap);
             S.hout[tid] = 0;
             if (tid < 4) atomicMax(&S.hw_halo, k);
         } else {
@@ -590,6 +601,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             S.n_leave = 0;
             if (n_leave > CO) atomicOr(&S.flags, kErrOutboxOverflow);
             ec[8] = min(n_leave, CO);
+            if (pec) pec[8] = min(n_leave, CO);
             P.tcount[done_lr * P.ntx + done_tc] = n_stay;
             S.hw_leave = max(S.hw_leave, n_leave);
         }
@@ -806,11 +818,16 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                     if (w_ | e_) { lists |= (e_ ? 3u : 2u) << (4 * nl); ++nl; }
                     if (nl == 2) { lists |= (4u + (s_ ? 2u : 0u) + (e_ ? 1u : 0u)) << 8; nl = 3; }
                     double2* ohxy = reinterpret_cast<double2*>(row_ptr(P.exp_out, P.L, lr) + P.L.off_hxy) + (size_t)tc * D::HL;
+                    char* prow = kPeer ? peer_row_of(P, lr) : nullptr;
+                    double2* phxy = prow ? reinterpret_cast<double2*>(prow + P.L.off_hxy) + (size_t)tc * D::HL : nullptr;
 #pragma unroll 1
                     for (int k = 0; k < nl; ++k) {
                         const int list = (int)((lists >> (4 * k)) & 15u);
                         const int idx = atomicAdd(&S.hout[list], 1);
-                        if (idx < halo_cap(list, HE, HC)) ohxy[halo_offset(list, HE, HC) + idx] = q;
+                        if (idx < halo_cap(list, HE, HC)) {
+                            ohxy[halo_offset(list, HE, HC) + idx] = q;
+                            if (phxy) phxy[halo_offset(list, HE, HC) + idx] = q;
+                        }
                     }
                 }
             } else if (valid) {
@@ -824,6 +841,9 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                     rec.id = id;
                     rec.row = nrow; rec.col = ncol; rec.pad = 0;
                     oobox[rank] = rec;
+                    if (kPeer) {
+                        if (char* prow = peer_row_of(P, lr)) (reinterpret_cast<OutRec*>(prow + P.L.off_obox) + (size_t)tc * CO)[rank] = rec;
+                    }
                 }
                 // a particle may not skip a whole tile in one step
                 if ((unsigned)(nrow - r0 + TS) >= (unsigned)(3 * TS) || (unsigned)(ncol - c0 + TS) >= (unsigned)(3 * TS))
@@ -1008,12 +1028,15 @@ struct TiledEngine {
     int parity = 0;
     bool acc_valid = false;    // acc holds the accelerations of the step that produced buffer [parity]
     bool ghost_fresh = false;  // ghost rows hold the neighbours' exports of the current parity
+    int comm_reserve_ctas = 16;  // CTA slots left free for the exchange kernels in slab mode (PSIM_COMM_RESERVE)
     // gather scratch
     DeviceArena gmem;
     SoAView g{};
     int* g_cursor = nullptr;
     int g_capacity = 0;
 };
+
+void tiled_slab_rows(int ntx, int rank, int nranks, int* begin, int* end);
 
 static ExportLayout make_layout(int ntx, int hl, int co) {
     ExportLayout L{};
@@ -1048,32 +1071,53 @@ static TileParams make_params(psim_sim* sim, TiledEngine* e, int parity_in) {
     P.bincnt = sim->bincnt;
     P.size = sim->size;
     P.err = sim->d_err;
+    P.last_lrow = e->lrows;
+    P.peer_row[0] = P.peer_row[1] = nullptr;
+    if (sim->p2p) {
+        const int po = parity_in ^ 1;
+        if (sim->rank > 0) {
+            int b, en;
+            tiled_slab_rows(e->ntx, sim->rank - 1, sim->nranks, &b, &en);
+            P.peer_row[0] = sim->peer_exports[0][po] + e->L.row_bytes * (size_t)(en - b + 1);   // its upper ghost row
+        }
+        if (sim->rank < sim->nranks - 1) P.peer_row[1] = sim->peer_exports[1][po];              // its lower ghost row (row 0)
+    }
     return P;
 }
 
 template <int TS>
 static int launch_step(psim_sim* sim, TiledEngine* e, int parity_in, bool store_acc, int lrow0, int nrows, int row_stride,
-                       cudaStream_t s) {
+                       bool allow_peer, cudaStream_t s) {
     if (nrows <= 0) return PSIM_OK;
     TileParams P = make_params(sim, e, parity_in);
+    if (!allow_peer) P.peer_row[0] = P.peer_row[1] = nullptr;
     P.lrow0 = lrow0;
     P.row_stride = row_stride;
     P.ntiles = nrows * e->ntx;
-    const int grid = std::min(P.ntiles, e->sms * e->ctas_per_sm);
-    if (store_acc)
-        tile_step_kernel<TS, true><<<grid, TileCfg<TS>::THREADS + 32, sizeof(TileSmem<TS>), s>>>(P);
-    else
-        tile_step_kernel<TS, false><<<grid, TileCfg<TS>::THREADS + 32, sizeof(TileSmem<TS>), s>>>(P);
+    // slabs: leave a few CTA slots free so that the exchange kernels (NCCL send / recv on the high-priority stream) can
+    // become resident next to the persistent interior-row CTAs instead of waiting for them to finish
+    const int reserve = (sim->nranks > 1 && !sim->p2p) ? e->comm_reserve_ctas : 0;
+    const int grid = std::min(P.ntiles, std::max(e->sms, e->sms * e->ctas_per_sm - reserve));
+    const bool peer = P.peer_row[0] || P.peer_row[1];
+    constexpr int kThreads = TileCfg<TS>::THREADS + 32;
+    constexpr size_t kSmem = sizeof(TileSmem<TS>);
+    if (store_acc) {
+        if (peer) tile_step_kernel<TS, true, true><<<grid, kThreads, kSmem, s>>>(P);
+        else tile_step_kernel<TS, true, false><<<grid, kThreads, kSmem, s>>>(P);
+    } else {
+        if (peer) tile_step_kernel<TS, false, true><<<grid, kThreads, kSmem, s>>>(P);
+        else tile_step_kernel<TS, false, false><<<grid, kThreads, kSmem, s>>>(P);
+    }
     ++sim->launches;
     return PSIM_OK;
 }
 
 static int launch_step_ts(psim_sim* sim, TiledEngine* e, int parity_in, bool store_acc, int lrow0, int nrows, cudaStream_t s,
-                          int row_stride = 1) {
+                          int row_stride = 1, bool allow_peer = true) {
     switch (e->ts) {
-        case 16: return launch_step<16>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, s);
-        case 32: return launch_step<32>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, s);
-        case 64: return launch_step<64>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, s);
+        case 16: return launch_step<16>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, allow_peer, s);
+        case 32: return launch_step<32>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, allow_peer, s);
+        case 64: return launch_step<64>(sim, e, parity_in, store_acc, lrow0, nrows, row_stride, allow_peer, s);
     }
     return fail(PSIM_ERR_INVALID, "tile size %d not instantiated", e->ts);
 }
@@ -1087,13 +1131,19 @@ static int configure(TiledEngine* e) {
     e->hl = TileDims<TS>::HL;
     e->threads = TileCfg<TS>::THREADS + 32;
     e->smem = sizeof(TileSmem<TS>);
-    PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    PSIM_CUDA(cudaFuncSetAttribute(tile_step_kernel<TS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    auto prepare = [&](auto kernel) -> int {
+        PSIM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+        PSIM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        return PSIM_OK;
+    };
+    PSIM_TRY(prepare(tile_step_kernel<TS, true, true>));
+    PSIM_TRY(prepare(tile_step_kernel<TS, true, false>));
+    PSIM_TRY(prepare(tile_step_kernel<TS, false, true>));
+    PSIM_TRY(prepare(tile_step_kernel<TS, false, false>));
     int per_sm = 0;
-    PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_step_kernel<TS, false>, TileCfg<TS>::THREADS + 32, e->smem));
+    PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_step_kernel<TS, false, false>, TileCfg<TS>::THREADS + 32, e->smem));
     e->ctas_per_sm = std::max(1, per_sm);
+    if (const char* r = std::getenv("PSIM_COMM_RESERVE")) e->comm_reserve_ctas = std::max(0, std::atoi(r));
     if (const char* cap = std::getenv("PSIM_CTAS_PER_SM")) {   // tuning / profiling knob
         const int c = std::atoi(cap);
         if (c >= 1) e->ctas_per_sm = std::min(e->ctas_per_sm, c);
@@ -1209,9 +1259,25 @@ int tiled_step(psim_sim* sim, int nsteps, int flags) {
         const bool store = (flags & PSIM_STEP_ACCEL_ALL) || (!(flags & PSIM_STEP_ACCEL_NONE) && step == nsteps - 1);
         if (!slabs) {
             PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, e->lrows, s));
+        } else if (sim->p2p) {
+            // Slab step, peer-memory flavour: the first and last owned tile rows go first, and that launch stores their
+            // exports (halo lists + migrants) into the local buffers AND straight into the neighbours' ghost rows over
+            // NVLink; a flag then tells the neighbours that my boundary rows of this step are done, and the interior
+            // rows follow.  My boundary rows may start once both neighbours have flagged the previous step: their
+            // stores into my ghost rows are complete and they no longer read the ghost rows I am about to overwrite.
+            // No exchange kernel, no copy: the transfer is fused into the step kernel.
+            if (!e->ghost_fresh) {   // first step after create: the neighbours' initial exports travel once through NCCL
+                PSIM_TRY(tiled_exchange(sim, e->parity, s));
+                e->ghost_fresh = true;
+            }
+            PSIM_TRY(comm_p2p_wait(sim, s));
+            if (e->lrows <= 2) PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, e->lrows, s));
+            else PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, 2, s, e->lrows - 1));   // rows 1 and lrows, storing to the peers
+            PSIM_TRY(comm_p2p_signal(sim, s));
+            if (e->lrows > 2) PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 2, e->lrows - 2, s, 1, /*peer=*/false));
         } else {
-            // Slab step: the first and last owned tile rows go first; as soon as they are done
-            // their exports (halo lists + migrants) travel to the neighbours on the exchange stream while the
+            // Slab step, NCCL flavour: the first and last owned tile rows go first; as soon as they are
+            // done their exports (halo lists + migrants) travel to the neighbours on the exchange stream while the
             // interior rows are computed.  The next step's boundary rows wait for both.
             if (!e->ghost_fresh) {   // first step after create: the neighbours' initial exports
                 PSIM_TRY(tiled_exchange(sim, e->parity, s));
@@ -1255,6 +1321,7 @@ int tiled_view(psim_sim* sim, SoAView* out) {
         PSIM_TRY(tiled_exchange(sim, e->parity, s));
         e->ghost_fresh = true;
     }
+    if (sim->p2p) PSIM_TRY(comm_p2p_wait(sim, s));   // the neighbours' stores into my ghost rows are complete
     TileParams P = make_params(sim, e, e->parity);
     tile_gather_kernel<<<e->lrows_alloc * e->ntx, 128, 0, s>>>(P, e->acc, e->ts, e->cap, e->co, e->tr_begin, e->tr_end,
                                                                e->acc_valid, e->g.x, e->g.y, e->g.vx, e->g.vy, e->g.ax,
@@ -1320,6 +1387,25 @@ void tiled_info(psim_sim* sim, psim_info_t* out) {
 }
 
 // accessors for psim_comm.cpp
+void tiled_export_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, size_t* row_bytes, int* lrows, int* ntx) {
+    TiledEngine* e = sim->tiled;
+    *parity0 = e->exports[0];
+    *parity1 = e->exports[1];
+    *bytes = e->export_bytes;
+    *row_bytes = e->L.row_bytes;
+    *lrows = e->lrows;
+    *ntx = e->ntx;
+}
+
+// one thread: publish my finished step count in the neighbours' flag words (peer memory); the preceding kernel's
+// stores are already visible system-wide at its completion, the fence orders the flag behind them
+__global__ void flag_store_kernel(int* flag_a, int* flag_b, int value) {
+    __threadfence_system();
+    if (flag_a) *reinterpret_cast<volatile int*>(flag_a) = value;
+    if (flag_b) *reinterpret_cast<volatile int*>(flag_b) = value;
+}
+void launch_flag_store(int* flag_a, int* flag_b, int value, cudaStream_t s) { flag_store_kernel<<<1, 1, 0, s>>>(flag_a, flag_b, value); }
+
 void tiled_boundary_rows(psim_sim* sim, int parity, char** first_owned, char** last_owned, char** ghost_lo, char** ghost_hi,
                          size_t* row_bytes) {
     TiledEngine* e = sim->tiled;
