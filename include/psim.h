@@ -153,6 +153,10 @@ int psim_init_particles(particle_t* parts_host, int num_parts, double size, int 
 int psim_save_frame(void* file, const double* xy, int num_parts, double size, int first);
 
 /* ---- multi-GPU slab exchange (one process per GPU) ---- */
+/* The slab decomposition the engine uses (precedent: reference part2/mpi.cpp:258-270, rows of cells along x split
+ * contiguously over the ranks): cell rows [*row_begin, *row_end) of a box with `bin_count` cells per side belong to
+ * `rank` of `nranks` when tiles are `tile_cells` cells wide (0 = the engine's default for that box).  Host only. */
+int psim_slab_rows(int bin_count, int tile_cells, int rank, int nranks, int* row_begin, int* row_end);
 /* 128-byte NCCL unique id: rank 0 creates it, the launcher broadcasts it, every rank connects. */
 int psim_comm_unique_id(unsigned char id128[128]);
 int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]);

@@ -11,7 +11,7 @@
  * Parity pin: the reference ships no tests, golden vectors or fixtures for this path
  * (SURVEY.md section 4), so this restatement is pinned against the reference ITSELF:
  * oracle/Makefile compiles the unmodified /root/reference/part1/{serial,reference}.cpp
- * into oracle/_ref/ and tests/test_oracle_vs_reference.py checks this file against
+ * into oracle/_ref/ and tests/test_oracle_cpu.py checks this file against
  * them in memory (bit-exact cell ids / counts, bit-exact states for particles with
  * at most two in-range neighbours, <= 1e-12 relative otherwise), and against the
  * committed fixtures in tests/golden/ that gen_golden.py produced from those binaries.

@@ -558,6 +558,10 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
 
         issue_tile<TS>(P, walk.coord(P), S.st[0], S.cnts[0], &S.full[0], lane < 18 ? load_count<TS>(P, walk.coord(P), lane) : 0, lane);
         ingest(0, walk.coord(P), 0u);
+#ifdef PSIM_PHASE_TIMERS
+        unsigned tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned tlast = (unsigned)clock();
+#endif
         for (int it = 0;; ++it) {
             const int t = first + it * G;
             if (t >= P.ntiles) break;
@@ -567,11 +571,19 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             const TileCoord cn = walk.coord(P);
             int cj_next = 0;
             if (has_next && lane < 18) cj_next = load_count<TS>(P, cn, lane);   // in flight across the barrier
+            PSIM_TICK(0);
             named_sync<kBarTable, T + 32>();   // every consumer warp has left tile it - 1: its stage is free
+            PSIM_TICK(1);
             if (has_next) issue_tile<TS>(P, cn, S.st[sb ^ 1], S.cnts[sb ^ 1], &S.full[sb ^ 1], cj_next, lane);
+            PSIM_TICK(2);
             named_sync<kBarForces, T + 32>();  // the consumers have cleaned the other cell table and are done with rel / pcell
+            PSIM_TICK(3);
             if (has_next) ingest(sb ^ 1, cn, (unsigned)(((it + 1) >> 1) & 1));
+            PSIM_TICK(4);
         }
+#ifdef PSIM_PHASE_TIMERS
+        if (lane == 0) for (int k = 0; k < 9; ++k) atomicAdd(&g_phase_cycles[33][k], (unsigned long long)tacc[k]);
+#endif
         return;
     }
 
@@ -1160,15 +1172,17 @@ void tiled_slab_rows(int ntx, int rank, int nranks, int* begin, int* end) {
     *end = *begin + q + (rank < r ? 1 : 0);
 }
 
+int tiled_default_tile(int bincnt) {
+    const long long cells = (long long)bincnt * bincnt;
+    return cells >= 32ll * 32 * 148 * 4 ? 32 : 16;
+}
+
 int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts, int n, bool parts_on_device,
                  bool* unsuitable) {
     *unsuitable = false;
     cudaStream_t s = sim->stream;
     int ts = cfg->tile_cells;
-    if (ts == 0) {
-        const long long cells = (long long)sim->bincnt * sim->bincnt;
-        ts = cells >= 32ll * 32 * 148 * 4 ? 32 : 16;
-    }
+    if (ts == 0) ts = tiled_default_tile(sim->bincnt);
     if (ts != 16 && ts != 32 && ts != 64) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32 or 64 (got %d)", ts);
     auto* e = new TiledEngine();
     sim->tiled = e;
@@ -1345,7 +1359,7 @@ void tiled_destroy(psim_sim* sim) {
         cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof h);
         const double tiles = (double)e->lrows * e->ntx * (double)std::max<long long>(sim->steps_done, 1);
         const char* names[9] = {"top", "wait_full", "A", "bar1", "B", "bar2", "C", "bar3", "DE"};
-        const char* pnames[9] = {"top", "bar1", "issue", "bar2", "wait_full", "ingest", "-", "-", "-"};
+        const char* pnames[9] = {"top", "bar1", "issue", "bar3", "wait+ingest", "-", "-", "-", "-"};
         for (int w = 0; w < 34; ++w) {
             if (w == 33) for (int k = 0; k < 9; ++k) names[k] = pnames[k];
             if (h[w][0] + h[w][2] == 0) continue;
@@ -1385,6 +1399,25 @@ void tiled_info(psim_sim* sim, psim_info_t* out) {
     out->outbox_capacity = e->co;
     out->halo_list_capacity = e->he;
 }
+
+}  // namespace psim
+
+extern "C" int psim_slab_rows(int bin_count, int tile_cells, int rank, int nranks, int* row_begin, int* row_end) {
+    using namespace psim;
+    if (bin_count < 1 || nranks < 1 || rank < 0 || rank >= nranks || !row_begin || !row_end)
+        return fail(PSIM_ERR_INVALID, "psim_slab_rows: bad argument");
+    const int ts = tile_cells ? tile_cells : tiled_default_tile(bin_count);
+    if (ts != 16 && ts != 32 && ts != 64) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32 or 64 (got %d)", ts);
+    const int ntx = tiled_tile_rows(bin_count, ts);
+    if (nranks > ntx) return fail(PSIM_ERR_INVALID, "more slabs (%d) than tile rows (%d)", nranks, ntx);
+    int b, e;
+    tiled_slab_rows(ntx, rank, nranks, &b, &e);
+    *row_begin = b * ts;
+    *row_end = std::min(e * ts, bin_count);
+    return PSIM_OK;
+}
+
+namespace psim {
 
 // accessors for psim_comm.cpp
 void tiled_export_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, size_t* row_bytes, int* lrows, int* ntx) {

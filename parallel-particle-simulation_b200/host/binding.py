@@ -30,7 +30,7 @@ DECLARED_SYMBOLS = [
     "psim_error_string", "psim_last_error", "psim_config_default", "psim_bin_count", "psim_create",
     "psim_destroy", "psim_step", "psim_sync", "psim_read_particles", "psim_read_positions",
     "psim_read_cells", "psim_read_cell_lists", "psim_stats", "psim_info", "psim_init_particles",
-    "psim_save_frame", "psim_comm_unique_id", "psim_comm_connect",
+    "psim_save_frame", "psim_comm_unique_id", "psim_comm_connect", "psim_slab_rows",
 ]
 
 
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.psim_save_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
     L.psim_comm_unique_id.argtypes = [C.c_void_p]
     L.psim_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
+    L.psim_slab_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -223,6 +224,13 @@ class Simulation:
             self.close()
         except Exception:
             pass
+
+
+def slab_rows(bin_count_: int, rank: int, nranks: int, tile_cells: int = 0) -> tuple[int, int]:
+    """cell rows [begin, end) of slab `rank` (host-side arithmetic only; reference precedent part2/mpi.cpp:258-270)"""
+    b, e = C.c_int(), C.c_int()
+    _check(lib().psim_slab_rows(bin_count_, tile_cells, rank, nranks, C.byref(b), C.byref(e)), "psim_slab_rows")
+    return b.value, e.value
 
 
 def comm_unique_id() -> bytes:
