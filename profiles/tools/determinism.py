@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Race hunt without a sanitizer: the same simulation under different schedules (CTAs per SM, tile size, engine) must
+end in bit-identical states (the summation order is canonical, so any difference is a race or a lost update)."""
+import hashlib, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    n, steps, tile, engine = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+    parts = pkg.init_particles(n, 42)
+    sim = pkg.Simulation(parts, n, pkg.box_size(n), engine=pkg.ENGINE_TILED if engine == "tiled" else pkg.ENGINE_CELLSORT, tile_cells=tile)
+    out = sim.step(steps).sync().read_particles()
+    print("HASH", hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest(), sim.info()["reserved_hw_pairs"])
+    sys.exit(0)
+n, steps = int(sys.argv[1]), int(sys.argv[2])
+hashes = {}
+for name, env, tile, engine in [("t32 4cta", {}, 32, "tiled"), ("t32 4cta again", {}, 32, "tiled"), ("t32 1cta", {"PSIM_CTAS_PER_SM": "1"}, 32, "tiled"),
+                                ("t32 3cta", {"PSIM_CTAS_PER_SM": "3"}, 32, "tiled"), ("t16", {}, 16, "tiled"), ("t64", {}, 64, "tiled"),
+                                ("cellsort", {}, 0, "cellsort")]:
+    r = subprocess.run([sys.executable, __file__, "child", str(n), str(steps), str(tile), engine], capture_output=True, text=True,
+                       env=dict(os.environ, **env))
+    line = [l for l in r.stdout.splitlines() if l.startswith("HASH")]
+    hashes[name] = line[0].split()[1] if line else "FAILED " + r.stderr[-300:]
+    print(f"{name:16s} {hashes[name][:32]}", flush=True)
+print("ALL_IDENTICAL", len(set(hashes.values())) == 1)
