@@ -402,8 +402,9 @@ static __device__ __noinline__ double2 slow_force(const double2* xy, const unsig
 #ifdef PSIM_PHASE_TIMERS
 // profiling build only: cycles spent per phase, summed over tiles, for warp 0, a middle warp and the loader warp
 __device__ unsigned long long g_phase_cycles[34][12];
-__device__ unsigned g_hist[4][64];   // histograms (256-cycle bins) of per-warp per-tile durations: 0 A, 1 B, 2 DE, 3 top+wait
+__device__ unsigned g_hist[8][64];   // histograms (256-cycle bins) of per-warp per-tile durations: 0 A, 1 B, 2 DE, 3 top+wait
 #define PSIM_HIST(h, k) do { if (lane == 0) atomicAdd(&g_hist[h][min((tacc[k] - hprev[k]) >> 8, 63u)], 1u); hprev[k] = tacc[k]; } while (0)
+#define PSIM_HIST_KEEP(h, k) do { if (lane == 0) atomicAdd(&g_hist[h][min((tacc[k] - hprev[k]) >> 8, 63u)], 1u); } while (0)
 #define PSIM_TICK(k)                                   \
     do {                                               \
         /* a barrier only blocks at the next access to shared memory: force one before reading the clock */ \
@@ -415,6 +416,7 @@ __device__ unsigned g_hist[4][64];   // histograms (256-cycle bins) of per-warp 
 #else
 #define PSIM_TICK(k) do {} while (0)
 #define PSIM_HIST(h, k) do {} while (0)
+#define PSIM_HIST_KEEP(h, k) do {} while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -450,6 +452,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
     // named barriers: 1 = cell table complete (consumers + producer), 2 = pair list complete (consumers),
     // 3 = pair contributions ready and the other cell table clean (consumers + producer)
     constexpr int kBarTable = 1, kBarPairs = 2, kBarForces = 3;
+    constexpr int TA = (NW - 1) * 32;   // consumer threads that bin (all warps but the last, which evaluates the pairs)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem<TS>& S = *reinterpret_cast<TileSmem<TS>*>(smem_raw);
@@ -533,6 +536,15 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                     const OutRec* grec = reinterpret_cast<const OutRec*>(row_ptr(P.exp_in, P.L, c.lr + nb / 3 - 1) + P.L.off_obox) +
                                          (size_t)(c.tc + nb % 3 - 1) * CO;
                     for (int e0 = s0; e0 < n; e0 += 32) take(e0 + lane < n, grec + min(e0 + lane, n - 1));
+                }
+            }
+            // own particles past the slots the consumer warps bin themselves (one slot per binning thread)
+            {
+                const int n_own0 = cnt[0];
+#pragma unroll 1
+                for (int p = TA + lane; p < n_own0; p += 32) {
+                    const double2 a = st.xy[p];
+                    bin_particle<TS, false>(S, sb, p, a.x, a.y, r0 - 1, c0 - 1, P.bincnt);
                 }
             }
             // the halo-list apron (already in place behind the own particles)
@@ -624,6 +636,19 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
     unsigned hprev[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     unsigned tlast = (unsigned)clock();
 #endif
+    // Phase A of a tile -- binning the particles that were already there, one per thread of the first NW-1 warps (the
+    // producer bins the rest, the migrants and the apron) -- runs during the PREVIOUS tile's pair-evaluation phase,
+    // when these warps would otherwise idle; only the first tile is binned up front.
+    auto bin_own = [&](int sb_, unsigned full_parity, int r0_, int c0_) {
+        if (warp < NW - 1) {
+            mbar_wait(&S.full[sb_], full_parity);   // the tile's bytes (and counts) have landed
+            if (tid < S.cnts[sb_][0]) {
+                const double2 a = S.st[sb_].xy[tid];
+                bin_particle<TS, false>(S, sb_, tid, a.x, a.y, r0_ - 1, c0_ - 1, P.bincnt);
+            }
+        }
+    };
+    bin_own(0, 0u, (P.tr_base + walk.lr) * TS, walk.tc * TS);
     for (int it = 0;; ++it) {
         if (first + it * G >= P.ntiles) break;
         const int sb = it & 1;   // stage and cell-table buffer of this tile
@@ -634,24 +659,22 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         const int r0 = tr * TS, c0 = tc * TS;
 
         PSIM_TICK(0);
-        mbar_wait(&S.full[sb], (unsigned)((it >> 1) & 1));  // this tile's bytes (and counts) have landed
         PSIM_TICK(1);
-
-        // ---- A: bin the particles that were already here (the producer warp bins the migrants and the apron
-        //      concurrently; the table only takes atomics) ------------------------------------------------------
-        {
-            const int n_own0 = S.cnts[sb][0];
-#pragma unroll 1
-            for (int p = tid; p < n_own0; p += T) {
-                const double2 a = st.xy[p];
-                bin_particle<TS, false>(S, sb, p, a.x, a.y, r0 - 1, c0 - 1, P.bincnt);
-            }
-        }
         PSIM_TICK(2);
         named_sync<kBarTable, T + 32>();   // (1) cell table complete; every warp has left the previous tile
         PSIM_TICK(3);
         if (tid < 9) publish_counts();
         const int n_own = S.n_own[sb];
+        // the other cell table (last read before this barrier) is cleaned now: the next tile is binned into it during
+        // this tile's pair-evaluation phase
+        {
+            unsigned* oh = S.head[sb ^ 1];
+            unsigned* ob = S.rowbits[sb ^ 1];
+#pragma unroll 1
+            for (int c = tid; c < NC; c += T) oh[c] = kEmpty;
+#pragma unroll 1
+            for (int c = tid; c < W * RW; c += T) ob[c] = 0u;
+        }
 
         // ---- B: candidate search in FP32 ------------------------------------------------------------------
 #pragma unroll 1
@@ -710,11 +733,12 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         named_sync<kBarPairs, T>();   // (2) pair list complete
         PSIM_TICK(5);
 
-        // ---- C: exact pair evaluation, one lane per pair (the last warps first: they have the fewest particles);
-        //      everybody else cleans the other cell table (last read before barrier 1) for the next tile ----------
-        {
+        // ---- C: exact pair evaluation by the last warp, one lane per pair; meanwhile the other warps bin the NEXT tile's
+        //      particles into the other cell table (phase A of the next tile) ----------------------------------------
+        if (warp == NW - 1) {
             const int np = min(S.npairs, NP);
-            for (int u = T - 1 - tid; u < np; u += T) {
+#pragma unroll 1
+            for (int u = lane; u < np; u += 32) {
                 const unsigned ij = S.pij[u];
                 PSIM_GUARD((ij & 0xFFFFu) < (unsigned)D::PTOT && (ij >> 16) < (unsigned)D::PTOT, 2, continue)
                 const double2 a = st.xy[ij & 0xFFFFu], b = st.xy[ij >> 16];
@@ -724,27 +748,29 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
                 if (!(r2 > kCutoff2) && r2 != 0.0) pair_contrib(dx, dy, r2, cx, cy);
                 S.pres[u] = make_double2(cx, cy);   // (+0, +0) for a prefilter false positive: neutral in the sum
             }
-            if (!kStoreAcc) {
-                // particles on the exact path (three or more candidates, or no room in the pair list): rare, and the
-                // only code with calls -- kept out of the move phase.  The acceleration is folded into the velocity
-                // right here (same two roundings as move_particle), the move phase then skips that update.
+        } else if (first + (it + 1) * G < P.ntiles) {
+            TileWalker nxt = walk;
+            nxt.advance(P);
+            bin_own(sb ^ 1, (unsigned)(((it + 1) >> 1) & 1), (P.tr_base + nxt.lr) * TS, nxt.tc * TS);
+        }
+        if (!kStoreAcc) {
+            // particles on the exact path (three or more candidates, or no room in the pair list): rare, and the
+            // only code with calls -- kept out of the move phase.  The acceleration is folded into the velocity
+            // right here (same two roundings as move_particle), the move phase then skips that update.
 #pragma unroll 1
-                for (int i = tid; i < n_own; i += T) {
-                    if (S.pcode[i] != 3u) continue;
-                    const double2 a = slow_force<W>(st.xy, head, next, i, S.pcell[i]);
-                    double2 v = st.v[i];
-                    v.x = __dadd_rn(v.x, __dmul_rn(a.x, kDt));
-                    v.y = __dadd_rn(v.y, __dmul_rn(a.y, kDt));
-                    st.v[i] = v;
-                    S.pcode[i] = 4u;   // velocity already advanced
-                }
+            for (int i = tid; i < n_own; i += T) {
+                if (S.pcode[i] != 3u) continue;
+                // (the cell is recomputed: pcell already holds the next tile's entries)
+                const double2 pi = st.xy[i];
+                int srow, scol;
+                cell_of(pi.x, pi.y, P.bincnt, srow, scol);
+                const double2 a = slow_force<W>(st.xy, head, next, i, (srow - (r0 - 1)) * W + (scol - (c0 - 1)));
+                double2 v = st.v[i];
+                v.x = __dadd_rn(v.x, __dmul_rn(a.x, kDt));
+                v.y = __dadd_rn(v.y, __dmul_rn(a.y, kDt));
+                st.v[i] = v;
+                S.pcode[i] = 4u;   // velocity already advanced
             }
-            unsigned* oh = S.head[sb ^ 1];
-            unsigned* ob = S.rowbits[sb ^ 1];
-#pragma unroll 1
-            for (int c = tid; c < NC; c += T) oh[c] = kEmpty;
-#pragma unroll 1
-            for (int c = tid; c < W * RW; c += T) ob[c] = 0u;
         }
         PSIM_TICK(6);
         named_sync<kBarForces, T + 32>();   // (3) contributions ready, other table clean
@@ -758,6 +784,9 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
 
         // ---- D: sum, move, new cell; E: re-tile (stayers -> other stripe buffer, leavers -> outbox, boundary
         //      cells -> halo lists).  No barrier in between: slots come from warp-aggregated atomics. -----------
+#ifdef PSIM_PHASE_TIMERS
+        int dbg_class = 0;
+#endif
         const size_t gbase = (size_t)(lr * P.ntx + tc) * CAP;
 #pragma unroll 1
         for (int i0 = 0; i0 < n_own; i0 += T) {   // uniform trip count: the ballots below need whole warps
@@ -811,6 +840,13 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             }
             sbase = __shfl_sync(0xffffffffu, sbase, 0);
             if (lm) lbase = __shfl_sync(0xffffffffu, lbase, 0);
+#ifdef PSIM_PHASE_TIMERS
+            {
+                const int er_ = nrow - r0, ec_ = ncol - c0;
+                const bool corner_ = stay && (er_ == 0 || er_ == TS - 1) && (ec_ == 0 || ec_ == TS - 1);
+                dbg_class |= (lm ? 1 : 0) | (__any_sync(0xffffffffu, corner_) ? 2 : 0);
+            }
+#endif
             PSIM_GUARD(!stay || (unsigned)(sbase + __popc(sm & lt_mask)) < (unsigned)CAP, 4, stay = false)
             if (stay) {
                 const double2 q = make_double2(x, y);
@@ -866,6 +902,7 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         PSIM_TICK(8);
         PSIM_HIST(0, 2);
         PSIM_HIST(1, 4);
+        PSIM_HIST_KEEP(4 + (dbg_class & 3), 8);
         PSIM_HIST(2, 8);
         PSIM_HIST(3, 1);
     }
@@ -1371,10 +1408,10 @@ void tiled_destroy(psim_sim* sim) {
             }
             std::fprintf(stderr, " total=%.0f\n", tot);
         }
-        unsigned hh[4][64];
+        unsigned hh[8][64];
         cudaMemcpyFromSymbol(hh, g_hist, sizeof hh);
-        const char* hn[4] = {"A", "B", "DE", "wait_full"};
-        for (int a = 0; a < 4; ++a) {
+        const char* hn[8] = {"A", "B", "DE", "wait_full", "DE plain", "DE leaver", "DE corner", "DE leaver+corner"};
+        for (int a = 0; a < 8; ++a) {
             std::fprintf(stderr, "[hist %s, 256-cycle bins]", hn[a]);
             for (int b = 0; b < 64; ++b) if (hh[a][b]) std::fprintf(stderr, " %d:%u", b, hh[a][b]);
             std::fprintf(stderr, "\n");
