@@ -157,6 +157,10 @@ static int p2p_setup(psim_sim* sim, ncclComm_t comm) {
         if (e != cudaSuccess) return fail(PSIM_ERR_COMM, "cudaIpcOpenMemHandle(neighbour flags): %s", cudaGetErrorString(e));
         sim->peer_flags[side] = static_cast<int*>(f);
     }
+    for (int k = 0; k < 2; ++k) {
+        PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_b[k], cudaEventDisableTiming));
+        PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_i[k], cudaEventDisableTiming));
+    }
     sim->p2p = true;
     sim->p2p_steps = 0;
     return PSIM_OK;
@@ -208,6 +212,11 @@ void comm_destroy(psim_sim* sim) {
     }
     if (sim->d_flags) cudaFree(sim->d_flags);
     sim->d_flags = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        if (sim->ev_b[k]) cudaEventDestroy(sim->ev_b[k]);
+        if (sim->ev_i[k]) cudaEventDestroy(sim->ev_i[k]);
+        sim->ev_b[k] = sim->ev_i[k] = nullptr;
+    }
     sim->p2p = false;
     if (sim->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(sim->comm));
     sim->comm = nullptr;

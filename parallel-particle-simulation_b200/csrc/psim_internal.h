@@ -126,6 +126,8 @@ struct psim_sim {
     char* peer_exports[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][parity]: neighbour's export buffers, mapped
     int* peer_flags[2] = {nullptr, nullptr};                               // [side]: neighbour's d_flags, mapped
     unsigned p2p_steps = 0;                 // steps signalled so far
+    cudaEvent_t ev_b[2] = {nullptr, nullptr};   // boundary launch of step s done (index s & 1)
+    cudaEvent_t ev_i[2] = {nullptr, nullptr};   // interior launch of step s done (index s & 1)
 };
 
 namespace psim {

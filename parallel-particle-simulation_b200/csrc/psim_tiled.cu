@@ -1321,11 +1321,26 @@ int tiled_step(psim_sim* sim, int nsteps, int flags) {
                 PSIM_TRY(tiled_exchange(sim, e->parity, s));
                 e->ghost_fresh = true;
             }
-            PSIM_TRY(comm_p2p_wait(sim, s));
-            if (e->lrows <= 2) PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, e->lrows, s));
-            else PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, 2, s, e->lrows - 1));   // rows 1 and lrows, storing to the peers
-            PSIM_TRY(comm_p2p_signal(sim, s));
+            // The boundary launch (stream B, high priority) and the interior launch (stream I = the handle's stream) of one
+            // step touch disjoint tiles and run CONCURRENTLY; each depends only on BOTH launches of the previous step:
+            //   boundary(s) after interior(s-1) [its rows 2 / lrows-1 exports], boundary(s-1), the neighbours' flags
+            //   interior(s) after boundary(s-1) [rows 1 / lrows exports], interior(s-1)
+            cudaStream_t sb = sim->comm_stream;
+            const unsigned k = sim->p2p_steps & 1u, kp = k ^ 1u;   // event slots of this step / the previous one
+            if (sim->p2p_steps == 0) {   // first step: everything enqueued so far on the handle's stream (create, initial exchange)
+                PSIM_CUDA(cudaEventRecord(sim->ev_i[kp], s));
+                PSIM_CUDA(cudaEventRecord(sim->ev_b[kp], s));
+            }
+            PSIM_CUDA(cudaStreamWaitEvent(sb, sim->ev_i[kp], 0));
+            PSIM_TRY(comm_p2p_wait(sim, sb));
+            if (e->lrows <= 2) PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, e->lrows, sb));
+            else PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 1, 2, sb, e->lrows - 1));   // rows 1 and lrows, storing to the peers
+            PSIM_CUDA(cudaEventRecord(sim->ev_b[k], sb));
+            PSIM_TRY(comm_p2p_signal(sim, sb));
+            PSIM_CUDA(cudaStreamWaitEvent(s, sim->ev_b[kp], 0));
             if (e->lrows > 2) PSIM_TRY(launch_step_ts(sim, e, e->parity, store, 2, e->lrows - 2, s, 1, /*peer=*/false));
+            PSIM_CUDA(cudaEventRecord(sim->ev_i[k], s));
+            if (step == nsteps - 1) PSIM_CUDA(cudaStreamWaitEvent(s, sim->ev_b[k], 0));   // the handle's stream covers the whole batch
         } else {
             // Slab step, NCCL flavour: the first and last owned tile rows go first; as soon as they are
             // done their exports (halo lists + migrants) travel to the neighbours on the exchange stream while the
