@@ -272,7 +272,8 @@ def main():
         "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n} particles, density 0.0005, cutoff 0.01, seed {args.seed} (BASELINE configs[3])",
+        "config": {"workload": f"{n} particles, density 0.0005, cutoff 0.01, seed {args.seed} "
+                               f"(BASELINE configs[{4 if args.scaling == 'weak' and world > 1 else 3 if n == 20_000_000 else 2 if n == 1_000_000 else 1 if n == 100_000 else '-'}])",
                    "particles": n, "engine": "tiled" if info["engine"] == pkg.ENGINE_TILED else "cellsort",
                    "tile_cells": info["tile_cells"], "slabs": world, "l2": "state (>= 640 MB per GPU at 20 M) larger than L2; no flush needed",
                    "accel_store": "last step of the batch", "device_bytes": info["device_bytes"]},

