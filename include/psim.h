@@ -23,7 +23,8 @@
  *                                               part3/gpu.cu:92-112 (Bins / Bin_Sizes)
  *   psim_stats             (no reference code; validation statistics of SURVEY.md section 8c-5)
  *   psim_init_particles    init_particles       part1/main.cpp:31-59
- *   psim_save_frame        save                 part1/main.cpp:15-28
+ *   psim_save_frame        save                 part1/main.cpp:15-28 (same bytes; std::to_chars formatter,
+ *                                               one fwrite per 64 k particles instead of a flush per line)
  */
 #ifndef PSIM_H
 #define PSIM_H
@@ -63,7 +64,7 @@ typedef struct psim_config {
     int   device;        /* CUDA device ordinal; -1 = the calling thread's current device        */
     void* stream;        /* cudaStream_t to run on; NULL = a private non-blocking stream         */
     int   tile_cells;    /* tiled engine: cutoff cells per tile side (16, 32 or 64); 0 = auto    */
-    int   use_graph;     /* tiled engine: replay steps through a CUDA graph (0/1); -1 = auto     */
+    int   use_graph;     /* reserved (ignored): steps are enqueued as plain launches, one per step */
     /* 1-D slab decomposition.  nranks == 1: the whole box.               */
     int   rank;          /* this slab's index along x (cell rows)                                */
     int   nranks;        /* number of slabs                                                      */

@@ -2,6 +2,8 @@
 // trajectory writer.  Both must reproduce the reference driver's observable behaviour exactly
 // (generator: same engine, same draw order, same distributions => same bits as reference
 // part1/main.cpp:31-59 when built against libstdc++; writer: the text format of part1/main.cpp:15-28).
+#include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -38,12 +40,35 @@ extern "C" int psim_init_particles(particle_t* parts, int num_parts, double size
     return PSIM_OK;
 }
 
+// One double in the reference's stream formatting (operator<< with the default precision 6 and neither fixed nor
+// scientific == printf("%g")).  std::to_chars with chars_format::general and precision 6 is specified to produce
+// exactly the characters of printf("%.6g") in the C locale, several times faster than the stdio formatter.
+static inline char* put_g6(char* p, char* end, double v) {
+    const std::to_chars_result r = std::to_chars(p, end, v, std::chars_format::general, 6);
+    return r.ptr;
+}
+
 extern "C" int psim_save_frame(void* file, const double* xy, int num_parts, double size, int first) {
     if (!file || (num_parts > 0 && !xy)) return psim::fail(PSIM_ERR_INVALID, "psim_save_frame: NULL argument");
     FILE* f = static_cast<FILE*>(file);
-    // default ostream formatting of the reference (precision 6, neither fixed nor scientific) == %g
     if (first) std::fprintf(f, "%d %g\n", num_parts, size);
-    for (int i = 0; i < num_parts; ++i) std::fprintf(f, "%g %g\n", xy[2 * i], xy[2 * i + 1]);
+    // format into a large buffer, one fwrite per chunk (the reference flushes every line through std::endl,
+    // part1/main.cpp:23: same bytes, far more system calls)
+    constexpr size_t kChunk = 1 << 16;                 // particles per buffer
+    std::vector<char> buf(kChunk * 64 + 64);           // two numbers of <= 24 characters, a blank and a newline
+    for (size_t i0 = 0; i0 < (size_t)num_parts; i0 += kChunk) {
+        const size_t i1 = std::min(i0 + kChunk, (size_t)num_parts);
+        char* p = buf.data();
+        char* const end = p + buf.size();
+        for (size_t i = i0; i < i1; ++i) {
+            p = put_g6(p, end, xy[2 * i]);
+            *p++ = ' ';
+            p = put_g6(p, end, xy[2 * i + 1]);
+            *p++ = '\n';
+        }
+        if (std::fwrite(buf.data(), 1, (size_t)(p - buf.data()), f) != (size_t)(p - buf.data()))
+            return psim::fail(PSIM_ERR_INVALID, "psim_save_frame: write failed");
+    }
     std::fputc('\n', f);
     return std::ferror(f) ? psim::fail(PSIM_ERR_INVALID, "psim_save_frame: write failed") : PSIM_OK;
 }

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <iostream>
 #include <vector>
 
@@ -67,14 +68,23 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     psim_sim* sim = nullptr;
     CHECK(psim_create(&sim, &cfg, parts.data(), num_parts, size));
-    std::vector<double> xy(fsave ? (size_t)num_parts * 2 : 0);
+    // Saves are pipelined: while a writer thread formats frame k (the dominant cost of -o at large N), the GPU
+    // already runs the next steps and the following frame lands in the other buffer.
+    std::vector<double> xy[2];
+    if (fsave) xy[0].resize((size_t)num_parts * 2), xy[1].resize((size_t)num_parts * 2);
+    std::future<int> writing;
+    int cur = 0;
     for (int step = 0; step < PSIM_NSTEPS; ++step) {
         CHECK(psim_step(sim, 1, step == PSIM_NSTEPS - 1 ? PSIM_STEP_DEFAULT : PSIM_STEP_ACCEL_NONE));
         if (fsave && (step % PSIM_SAVEFREQ) == 0) {
-            CHECK(psim_read_positions(sim, xy.data()));
-            CHECK(psim_save_frame(fsave, xy.data(), num_parts, size, step == 0));
+            CHECK(psim_read_positions(sim, xy[cur].data()));
+            if (writing.valid()) CHECK(writing.get());   // frames stay in order
+            writing = std::async(std::launch::async, psim_save_frame, (void*)fsave, (const double*)xy[cur].data(), num_parts, size,
+                                 step == 0 ? 1 : 0);
+            cur ^= 1;
         }
     }
+    if (writing.valid()) CHECK(writing.get());
     CHECK(psim_sync(sim));
     const auto t1 = std::chrono::steady_clock::now();
     const double seconds = std::chrono::duration<double>(t1 - t0).count();

@@ -134,3 +134,23 @@ def test_save_frame_matches_reference_text_format(pkg, tmp_path):
     lines = path.read_text().split("\n")
     assert lines[:4] == meta["head"]  # "1000 0.707107" + the first three particles of frame 0 (= state after step 1)
     assert len(lines) == 1000 + 3
+
+
+def test_save_frame_formatter_equals_printf_g(pkg, tmp_path):
+    """psim_save_frame formats with std::to_chars(general, 6); the reference streams doubles with the default ostream
+    precision, i.e. printf("%g").  Same characters on random and on awkward values."""
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.random(50000) * 300, 10.0 ** rng.uniform(-12, 3, 50000),
+                           [0.0, 1e-5, 9.99999e-5, 0.0001, 0.000123456789, 999999.5, 1e6, 123456.5, 0.1, 100.0, 99.99995,
+                            0.99999949, 5e-324, 1.0, 282.84271247461902, 0.70710678118654757]])
+    xy = np.ascontiguousarray(vals.reshape(-1, 2))
+    path = tmp_path / "f.txt"
+    f = libc.fopen(str(path).encode(), b"w")
+    assert pkg.lib().psim_save_frame(f, xy.ctypes.data, len(xy), 1.0, 0) == 0
+    libc.fclose(f)
+    got = path.read_text().split("\n")[:-2]
+    assert got == ["%g %g" % (a, b) for a, b in xy]
