@@ -75,6 +75,7 @@ template <int TS> struct TileDims {
     using C = TileCfg<TS>;
     static constexpr int W = TS + 2, NC = W * W;
     static constexpr int RW = (W + 31) / 32 + 1;          // occupancy words per cell row (+1: funnel shifts read one past)
+    static constexpr int NC4 = (NC + 3) / 4 * 4, RB4 = (W * RW + 3) / 4 * 4;   // table sizes padded to 16 bytes
     static constexpr int HL = 4 * C::HE + 4 * C::HC;      // halo entries a tile exports / stages
     static constexpr int MAXH = HL + 16;                  // apron capacity (halo lists + apron outbox records)
     static constexpr int PTOT = C::CAP + MAXH;
@@ -101,13 +102,15 @@ template <int TS> struct __align__(16) TileSmem {
     double2 pres[C::NP];                      // pair list: contribution of pair t to its first particle
     float2 rel[D::PTOT];                      // tile-relative FP32 positions in cell units (prefilter only; read before barrier 2,
                                               // the producer writes the next tile's after it)
-    unsigned head[2][D::NC];                  // per cell: first particle of its list (kEmpty: none); double buffered by tile
-    unsigned rowbits[2][D::W * D::RW];        // per cell row: occupancy bit per cell
+    // per cell: first particle of its list (kEmpty: none); per cell row: occupancy bit per cell.  Double buffered by tile,
+    // padded to whole 16-byte words so that a table is wiped with 128-bit stores
+    alignas(16) unsigned head[2][D::NC4];
+    alignas(16) unsigned rowbits[2][D::RB4];
     unsigned pij[C::NP];                      // pair list: i | j << 16
     unsigned long long full[2];               // mbarriers: stage filled by TMA
     unsigned short next[2][D::PTOT];          // next particle in the same cell (double buffered like head: the exact path of
                                               // a slow warp may still walk the lists while a fast warp bins the next tile)
-    unsigned short pcell[D::PTOT];            // cell of a binned particle (read before barrier 2, the producer writes the next
+    unsigned short pcell[D::PTOT];            // local row << 8 | local column of a binned particle (read before barrier 2, the producer writes the next
                                               // tile's after it)
     unsigned short pcode[C::CAP];             // per own particle: search result (pair count | pair-list base << 2), B -> D
     int cnts[2][32];                          // staged tiles: [0] own, [1..8] halo lists, [9..17] outboxes, [18] halo total,
@@ -438,7 +441,7 @@ __device__ __forceinline__ void bin_particle(TileSmem<TS>& S, int sb, int p, dou
     const int cell = lrow * D::W + lcol;
     const unsigned old = atomicExch(&S.head[sb][cell], (unsigned)p);
     S.next[sb][p] = (unsigned short)old;
-    S.pcell[p] = (unsigned short)cell;
+    S.pcell[p] = (unsigned short)((lrow << 8) | lcol);   // row and column separately: no division when it is read back
     atomicOr(&S.rowbits[sb][lrow * D::RW + (lcol >> 5)], 1u << (lcol & 31));
     S.rel[p] = make_float2(__double2float_rn(__dsub_rn(qx, (double)r0m1)), __double2float_rn(__dsub_rn(qy, (double)c0m1)));
 }
@@ -477,8 +480,8 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         S.prev_tc = 0;
     }
     if (tid < 8) S.hout[tid] = 0;
-    for (int c = tid; c < 2 * NC; c += T + 32) (&S.head[0][0])[c] = kEmpty;
-    for (int c = tid; c < 2 * W * RW; c += T + 32) (&S.rowbits[0][0])[c] = 0u;
+    for (int c = tid; c < 2 * D::NC4; c += T + 32) (&S.head[0][0])[c] = kEmpty;
+    for (int c = tid; c < 2 * D::RB4; c += T + 32) (&S.rowbits[0][0])[c] = 0u;
     __syncthreads();
 
     TileWalker walk;
@@ -668,19 +671,20 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
         // the other cell table (last read before this barrier) is cleaned now: the next tile is binned into it during
         // this tile's pair-evaluation phase
         {
-            unsigned* oh = S.head[sb ^ 1];
-            unsigned* ob = S.rowbits[sb ^ 1];
+            uint4* oh = reinterpret_cast<uint4*>(S.head[sb ^ 1]);
+            uint4* ob = reinterpret_cast<uint4*>(S.rowbits[sb ^ 1]);
 #pragma unroll 1
-            for (int c = tid; c < NC; c += T) oh[c] = kEmpty;
-#pragma unroll 1
-            for (int c = tid; c < W * RW; c += T) ob[c] = 0u;
+            for (int c = tid; c < D::NC4 / 4; c += T) oh[c] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            if (tid < D::RB4 / 4) ob[tid] = make_uint4(0u, 0u, 0u, 0u);
+            static_assert(D::RB4 / 4 <= T, "one 128-bit store per thread wipes the occupancy map");
         }
 
         // ---- B: candidate search in FP32 ------------------------------------------------------------------
 #pragma unroll 1
         for (int i = tid; i < n_own; i += T) {
-            const int cell = S.pcell[i];
-            const int lrow = cell / W, lcol = cell - lrow * W;
+            const int rc = S.pcell[i];
+            const int lrow = rc >> 8, lcol = rc & 0xFF;
+            const int cell = lrow * W + lcol;
             PSIM_GUARD(lrow >= 1 && lrow <= TS && lcol >= 1 && lcol <= TS, 0, continue)
             const float2 ri = S.rel[i];
             // 9 occupancy bits of the 3x3 neighbourhood, bit 3*(dr+1) + (dc+1)
