@@ -29,6 +29,8 @@
 #ifndef PSIM_H
 #define PSIM_H
 
+#include <stddef.h>
+
 #include "psim_common.h"
 
 #ifdef __cplusplus
@@ -108,6 +110,14 @@ const char* psim_error_string(int status);
 const char* psim_last_error(void);
 
 /* ---- lifecycle ---- */
+/* Create the CUDA context on `device` (-1: current) ahead of time.  The reference's CUDA driver pays this cost before
+ * its timer starts (its cudaMalloc at part3/main.cu:120-122 precedes the clock at :125); a host-pointer driver would
+ * otherwise pay it inside init_simulation.  Optional: psim_create does it implicitly. */
+int psim_device_init(int device);
+/* Page-lock (or release) a caller-owned host array so that the read-backs into it run at full PCIe speed.  Optional;
+ * the drop-in shim does it for the driver's `parts` array, which it is handed on every call anyway. */
+int psim_host_register(void* host_ptr, size_t bytes);
+int psim_host_unregister(void* host_ptr);
 void psim_config_default(psim_config* cfg);
 /* cells per side, ceil(size / 0.01): reference part1/serial.cpp:78 */
 int  psim_bin_count(double size);

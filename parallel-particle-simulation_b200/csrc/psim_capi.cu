@@ -209,6 +209,21 @@ static int check_device_error(psim_sim* sim) {
                 sim->h_err[4]);
 }
 
+// read-back staging buffer, kept between calls (the drop-in drivers read the state back every savefreq steps)
+static int ensure_scratch(psim_sim* sim, size_t bytes, void** out) {
+    if (sim->scratch_bytes < bytes) {
+        sim->scratch.release();
+        sim->scratch_ptr = nullptr;
+        sim->scratch_bytes = 0;
+        char* p = nullptr;
+        PSIM_TRY(sim->scratch.alloc(&p, bytes));
+        sim->scratch_ptr = p;
+        sim->scratch_bytes = bytes;
+    }
+    *out = sim->scratch_ptr;
+    return PSIM_OK;
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -253,6 +268,39 @@ void psim_config_default(psim_config* cfg) {
 }
 
 int psim_bin_count(double size) { return (int)std::ceil(size / PSIM_BIN_SIZE); }
+
+int psim_host_register(void* host_ptr, size_t bytes) {
+    if (!host_ptr || !bytes) return fail(PSIM_ERR_INVALID, "psim_host_register: NULL / empty");
+    if (pointer_on_device(host_ptr)) return PSIM_OK;   // nothing to pin
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return PSIM_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PSIM_ERR_CUDA, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    return PSIM_OK;
+}
+
+int psim_host_unregister(void* host_ptr) {
+    if (!host_ptr) return PSIM_OK;
+    if (cudaHostUnregister(host_ptr) != cudaSuccess) cudaGetLastError();
+    return PSIM_OK;
+}
+
+int psim_device_init(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PSIM_ERR_NO_DEVICE, "psim_device_init: no CUDA device visible; libpsim has no CPU fallback");
+    }
+    if (device >= ndev) return fail(PSIM_ERR_INVALID, "psim_device_init: device %d of %d", device, ndev);
+    if (device >= 0) PSIM_CUDA(cudaSetDevice(device));
+    PSIM_CUDA(cudaFree(nullptr));   // forces context creation
+    return PSIM_OK;
+}
 
 int psim_create(psim_sim** out, const psim_config* cfg_in, const particle_t* parts, int num_parts, double size) {
     if (!out) return fail(PSIM_ERR_INVALID, "psim_create: out is NULL");
@@ -395,10 +443,9 @@ int psim_read_particles(psim_sim* sim, particle_t* dst) {
         PSIM_CUDA(cudaStreamSynchronize(s));
         return PSIM_OK;
     }
-    sim->scratch.release();
     particle_t* stage = nullptr;
     if (sim->nranks == 1) {
-        PSIM_TRY(sim->scratch.alloc(&stage, (size_t)sim->n_total));
+        PSIM_TRY(ensure_scratch(sim, sizeof(particle_t) * (size_t)std::max(sim->n_total, 1), reinterpret_cast<void**>(&stage)));
         if (v.n) soa_to_aos_kernel<<<blocks, kObsThreads, 0, s>>>(v, acc, stage);
         ++sim->launches;
         PSIM_CUDA(cudaGetLastError());
@@ -406,7 +453,7 @@ int psim_read_particles(psim_sim* sim, particle_t* dst) {
         PSIM_CUDA(cudaStreamSynchronize(s));
     } else {
         // a slab writes only the records it owns: pack on the device, place on the host
-        PSIM_TRY(sim->scratch.alloc(&stage, (size_t)v.n));
+        PSIM_TRY(ensure_scratch(sim, sizeof(particle_t) * (size_t)std::max(v.n, 1), reinterpret_cast<void**>(&stage)));
         if (v.n) soa_pack_kernel<<<blocks, kObsThreads, 0, s>>>(v, acc, stage);
         ++sim->launches;
         std::vector<particle_t> rec((size_t)v.n);
@@ -416,7 +463,6 @@ int psim_read_particles(psim_sim* sim, particle_t* dst) {
         PSIM_CUDA(cudaStreamSynchronize(s));
         for (int i = 0; i < v.n; ++i) dst[ids[i]] = rec[i];
     }
-    sim->scratch.release();
     return PSIM_OK;
 }
 
@@ -436,9 +482,8 @@ int psim_read_positions(psim_sim* sim, double* xy) {
         PSIM_CUDA(cudaStreamSynchronize(s));
         return PSIM_OK;
     }
-    sim->scratch.release();
     double2* stage = nullptr;
-    PSIM_TRY(sim->scratch.alloc(&stage, (size_t)sim->n_total));
+    PSIM_TRY(ensure_scratch(sim, sizeof(double2) * (size_t)std::max(sim->n_total, 1), reinterpret_cast<void**>(&stage)));
     if (sim->nranks > 1)
         PSIM_CUDA(cudaMemcpyAsync(stage, xy, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyHostToDevice, s));
     if (v.n) soa_to_xy_kernel<<<blocks, kObsThreads, 0, s>>>(v, stage);
@@ -446,7 +491,6 @@ int psim_read_positions(psim_sim* sim, double* xy) {
     PSIM_CUDA(cudaGetLastError());
     PSIM_CUDA(cudaMemcpyAsync(xy, stage, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
     PSIM_CUDA(cudaStreamSynchronize(s));
-    sim->scratch.release();
     return PSIM_OK;
 }
 

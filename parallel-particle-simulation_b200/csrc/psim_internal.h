@@ -114,6 +114,8 @@ struct psim_sim {
     psim::TiledEngine* tiled = nullptr;
     // scratch for observation calls
     psim::DeviceArena scratch;
+    char* scratch_ptr = nullptr;
+    size_t scratch_bytes = 0;
     void* comm = nullptr;  // ncclComm_t when connected
     // slab exchange runs on its own stream so that it overlaps the interior tile rows of the same step
     cudaStream_t comm_stream = nullptr;

@@ -65,6 +65,7 @@ int main(int argc, char** argv) {
     }
     if (const char* t = std::getenv("PSIM_TILE")) cfg.tile_cells = std::atoi(t);
 
+    CHECK(psim_device_init(-1));   // context before the clock, like the reference's CUDA driver (part3/main.cu:120-125)
     const auto t0 = std::chrono::steady_clock::now();
     psim_sim* sim = nullptr;
     CHECK(psim_create(&sim, &cfg, parts.data(), num_parts, size));

@@ -27,7 +27,7 @@ STEP_DEFAULT, STEP_ACCEL_ALL, STEP_ACCEL_NONE = 0, 1, 2
 
 # every symbol include/psim.h declares (tests check that the library exports each of them)
 DECLARED_SYMBOLS = [
-    "psim_error_string", "psim_last_error", "psim_config_default", "psim_bin_count", "psim_create",
+    "psim_error_string", "psim_last_error", "psim_device_init", "psim_host_register", "psim_host_unregister", "psim_config_default", "psim_bin_count", "psim_create",
     "psim_destroy", "psim_step", "psim_sync", "psim_read_particles", "psim_read_positions",
     "psim_read_cells", "psim_read_cell_lists", "psim_stats", "psim_info", "psim_init_particles",
     "psim_save_frame", "psim_comm_unique_id", "psim_comm_connect", "psim_slab_rows",
