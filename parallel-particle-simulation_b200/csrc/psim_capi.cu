@@ -431,6 +431,21 @@ int psim_read_particles(psim_sim* sim, particle_t* dst) {
     if (!sim || !dst) return fail(PSIM_ERR_INVALID, "psim_read_particles: NULL argument");
     DeviceGuard g(sim->device);
     PSIM_TRY(check_device_error(sim));
+    if (sim->engine == PSIM_ENGINE_TILED && sim->nranks == 1) {
+        // one pass straight from the tiles into the caller's order (no intermediate compaction)
+        cudaStream_t s = sim->stream;
+        if (pointer_on_device(dst)) {
+            PSIM_TRY(tiled_writeback(sim, dst, nullptr));
+            PSIM_CUDA(cudaStreamSynchronize(s));
+            return PSIM_OK;
+        }
+        particle_t* stage = nullptr;
+        PSIM_TRY(ensure_scratch(sim, sizeof(particle_t) * (size_t)std::max(sim->n_total, 1), reinterpret_cast<void**>(&stage)));
+        PSIM_TRY(tiled_writeback(sim, stage, nullptr));
+        PSIM_CUDA(cudaMemcpyAsync(dst, stage, sizeof(particle_t) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        return PSIM_OK;
+    }
     SoAView v;
     bool acc;
     PSIM_TRY(view_of(sim, &v, &acc));
@@ -470,6 +485,20 @@ int psim_read_positions(psim_sim* sim, double* xy) {
     if (!sim || !xy) return fail(PSIM_ERR_INVALID, "psim_read_positions: NULL argument");
     DeviceGuard g(sim->device);
     PSIM_TRY(check_device_error(sim));
+    if (sim->engine == PSIM_ENGINE_TILED && sim->nranks == 1) {
+        cudaStream_t s = sim->stream;
+        if (pointer_on_device(xy)) {
+            PSIM_TRY(tiled_writeback(sim, nullptr, reinterpret_cast<double2*>(xy)));
+            PSIM_CUDA(cudaStreamSynchronize(s));
+            return PSIM_OK;
+        }
+        double2* stage = nullptr;
+        PSIM_TRY(ensure_scratch(sim, sizeof(double2) * (size_t)std::max(sim->n_total, 1), reinterpret_cast<void**>(&stage)));
+        PSIM_TRY(tiled_writeback(sim, nullptr, stage));
+        PSIM_CUDA(cudaMemcpyAsync(xy, stage, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        return PSIM_OK;
+    }
     SoAView v;
     bool acc;
     PSIM_TRY(view_of(sim, &v, &acc));

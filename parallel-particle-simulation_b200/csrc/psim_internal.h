@@ -43,10 +43,31 @@ enum : int {
 struct DeviceArena {
     std::vector<void*> ptrs;
     size_t bytes = 0;
+    // optional: one big block that the following alloc() calls carve up (a dozen multi-hundred-megabyte cudaMallocs cost
+    // tens of milliseconds inside the drivers' timed region; one does not)
+    char* block = nullptr;
+    size_t block_size = 0, block_used = 0;
+    int reserve(size_t total) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, total);
+        if (e != cudaSuccess) return fail(PSIM_ERR_CUDA, "cudaMalloc(%zu bytes): %s", total, cudaGetErrorString(e));
+        ptrs.push_back(q);
+        block = static_cast<char*>(q);
+        block_size = total;
+        block_used = 0;
+        bytes += total;
+        return PSIM_OK;
+    }
     template <class T>
     int alloc(T** p, size_t count) {
         *p = nullptr;
         if (count == 0) count = 1;
+        const size_t need = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (block && block_used + need <= block_size) {
+            *p = reinterpret_cast<T*>(block + block_used);
+            block_used += need;
+            return PSIM_OK;
+        }
         void* q = nullptr;
         cudaError_t e = cudaMalloc(&q, count * sizeof(T));
         if (e != cudaSuccess) return fail(PSIM_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
@@ -59,6 +80,8 @@ struct DeviceArena {
         for (void* q : ptrs) cudaFree(q);
         ptrs.clear();
         bytes = 0;
+        block = nullptr;
+        block_size = block_used = 0;
     }
 };
 
@@ -153,6 +176,7 @@ void tiled_export_buffers(psim_sim* sim, char** parity0, char** parity1, size_t*
 void launch_flag_store(int* flag_a, int* flag_b, int value, cudaStream_t s);   // psim_tiled.cu
 int tiled_step(psim_sim* sim, int nsteps, int flags);
 int tiled_view(psim_sim* sim, SoAView* out);  // gathers into scratch
+int tiled_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy);  // original-order write-back straight from the tiles
 void tiled_destroy(psim_sim* sim);
 long long tiled_bytes(psim_sim* sim);
 void tiled_info(psim_sim* sim, psim_info_t* out);

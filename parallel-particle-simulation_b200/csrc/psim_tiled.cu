@@ -1059,6 +1059,50 @@ __global__ void __launch_bounds__(128) tile_gather_kernel(const TileParams P, co
     }
 }
 
+// Write-back in ORIGINAL particle order straight from the tiles (the drivers' view of `parts`, reference
+// part1/main.cpp:135-136 / part3/main.cu:134-136): out[id] = {x y vx vy ax ay}, or only xy[id] = {x y}.  One CTA per
+// tile; particles still sitting in an outbox (they left their tile in the last step) are written by the tile that owns
+// the outbox.  Every owned particle is in exactly one stripe or one outbox, so no intermediate compaction is needed.
+__global__ void __launch_bounds__(128) tile_writeback_kernel(const TileParams P, const double2* __restrict__ acc, int cap, int co,
+                                                             int tr_begin, int tr_end, int ts, bool have_acc,
+                                                             particle_t* __restrict__ out, double2* __restrict__ out_xy) {
+    const int lr = blockIdx.x / P.ntx, tc = blockIdx.x % P.ntx;
+    const int tr = P.tr_base + lr;
+    const int lt = lr * P.ntx + tc;
+    const bool owned = tr >= tr_begin && tr < tr_end;
+    const int n_tile = owned ? min(P.tcount[lt], cap) : 0;
+    const size_t gbase = (size_t)lt * cap;
+    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) {
+        const int id = P.id_in[gbase + i];
+        const double2 p = P.pos_in[gbase + i];
+        if (out_xy) {
+            out_xy[id] = p;
+        } else {
+            double2* q = reinterpret_cast<double2*>(out + id);
+            q[0] = p;
+            q[1] = P.vel_in[gbase + i];
+            q[2] = have_acc ? acc[gbase + i] : make_double2(0.0, 0.0);
+        }
+    }
+    const bool row_valid = tr >= 0 && tr < P.nty;
+    const char* row = row_ptr(P.exp_in, P.L, lr);
+    const int n_out = row_valid ? min((reinterpret_cast<const int*>(row + P.L.off_cnt) + (size_t)tc * 16)[8], co) : 0;
+    const OutRec* ob = reinterpret_cast<const OutRec*>(row + P.L.off_obox) + (size_t)tc * co;
+    for (int k = threadIdx.x; k < n_out; k += blockDim.x) {
+        const OutRec r = ob[k];
+        const int dtr = r.row / ts;
+        if (dtr < tr_begin || dtr >= tr_end) continue;   // migrated to another slab
+        if (out_xy) {
+            out_xy[r.id] = make_double2(r.x, r.y);
+        } else {
+            double2* q = reinterpret_cast<double2*>(out + r.id);
+            q[0] = make_double2(r.x, r.y);
+            q[1] = make_double2(r.vx, r.vy);
+            q[2] = have_acc ? make_double2(r.ax, r.ay) : make_double2(0.0, 0.0);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1245,12 +1289,18 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     e->export_bytes = e->L.row_bytes * (size_t)e->lrows_alloc;
 
     const size_t slots = (size_t)e->lrows_alloc * e->ntx * e->cap;
+    // the export buffers are separate allocations (their CUDA IPC handles are shared with the neighbour slabs) ...
+    for (int b = 0; b < 2; ++b) {
+        PSIM_TRY(e->mem.alloc(&e->exports[b], e->export_bytes));
+        PSIM_CUDA(cudaMemsetAsync(e->exports[b], 0, e->export_bytes, s));
+    }
+    // ... everything else comes out of one block
+    PSIM_TRY(e->mem.reserve(slots * (2 * (2 * sizeof(double2) + sizeof(int)) + sizeof(double2)) +
+                            sizeof(int) * (size_t)e->lrows_alloc * e->ntx + 16 * 256));
     for (int b = 0; b < 2; ++b) {
         PSIM_TRY(e->mem.alloc(&e->pos[b], slots));
         PSIM_TRY(e->mem.alloc(&e->vel[b], slots));
         PSIM_TRY(e->mem.alloc(&e->sid[b], slots));
-        PSIM_TRY(e->mem.alloc(&e->exports[b], e->export_bytes));
-        PSIM_CUDA(cudaMemsetAsync(e->exports[b], 0, e->export_bytes, s));
     }
     PSIM_TRY(e->mem.alloc(&e->acc, slots));
     PSIM_TRY(e->mem.alloc(&e->tcount, (size_t)e->lrows_alloc * e->ntx));
@@ -1261,7 +1311,7 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     {
         DeviceArena stage;
         particle_t* d_stage = nullptr;
-        const int chunk = parts_on_device ? n : std::min(n, 8 << 20);
+        const int chunk = parts_on_device ? n : std::min(n, 4 << 20);
         if (!parts_on_device && n > 0) PSIM_TRY(stage.alloc(&d_stage, (size_t)chunk));
         for (int off = 0; off < n; off += chunk) {
             const int m = std::min(chunk, n - off);
@@ -1273,10 +1323,10 @@ int tiled_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
             tile_fill_kernel<<<(m + 255) / 256, 256, 0, s>>>(src, m, off, sim->bincnt, ts, e->cap, e->ntx, e->tr_begin,
                                                              e->tr_end, e->tr_begin - 1, e->pos[0], e->vel[0], e->sid[0],
                                                              e->tcount, sim->d_err);
-            ++sim->launches;
-            if (!parts_on_device) PSIM_CUDA(cudaStreamSynchronize(s));
+            ++sim->launches;   // (no host synchronisation per chunk: copy and kernel are ordered by the stream)
         }
         PSIM_CUDA(cudaGetLastError());
+        if (!parts_on_device) PSIM_CUDA(cudaStreamSynchronize(s));   // the staging buffer is freed below
         stage.release();
     }
     // suitability: the densest tile must leave headroom for fluctuations, else the caller falls back
@@ -1405,6 +1455,23 @@ int tiled_view(psim_sim* sim, SoAView* out) {
     PSIM_CUDA(cudaStreamSynchronize(s));
     *out = e->g;
     out->n = n;
+    return PSIM_OK;
+}
+
+// original-order write-back into a DEVICE buffer of n_total records (exactly one of d_out / d_xy); enqueued on the handle's stream
+int tiled_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy) {
+    TiledEngine* e = sim->tiled;
+    cudaStream_t s = sim->stream;
+    if (sim->nranks > 1 && !e->ghost_fresh) {
+        PSIM_TRY(tiled_exchange(sim, e->parity, s));
+        e->ghost_fresh = true;
+    }
+    if (sim->p2p) PSIM_TRY(comm_p2p_wait(sim, s));
+    TileParams P = make_params(sim, e, e->parity);
+    tile_writeback_kernel<<<e->lrows_alloc * e->ntx, 128, 0, s>>>(P, e->acc, e->cap, e->co, e->tr_begin, e->tr_end, e->ts,
+                                                                  e->acc_valid, d_out, d_xy);
+    ++sim->launches;
+    PSIM_CUDA(cudaGetLastError());
     return PSIM_OK;
 }
 
