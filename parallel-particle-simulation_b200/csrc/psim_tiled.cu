@@ -450,7 +450,7 @@ template <int TS, bool kStoreAcc, bool kPeer>
 __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) tile_step_kernel(const TileParams P) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
-    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, NC = D::NC, RW = D::RW, NW = D::NW;
+    constexpr int T = C::THREADS, CAP = C::CAP, W = D::W, RW = D::RW, NW = D::NW;
     constexpr int HE = C::HE, HC = C::HC, CO = C::CO, NP = C::NP;
     // named barriers: 1 = cell table complete (consumers + producer), 2 = pair list complete (consumers),
     // 3 = pair contributions ready and the other cell table clean (consumers + producer)
