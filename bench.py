@@ -242,9 +242,7 @@ def main():
             sim2 = pkg.Simulation(host, n, size, engine=engine, device=local, stream=stream.cuda_stream,
                                   tile_cells=args.tile, rank=rank, nranks=world)
             if world > 1:
-                uid = [pkg.comm_unique_id() if rank == 0 else None]
-                dist.broadcast_object_list(uid, src=0)
-                sim2.comm_connect(uid[0])
+                sim2.comm_connect(uid[0])   # same id: the process-level communicator is reused (like MPI_COMM_WORLD)
             sim2.step(args.steps, pkg.STEP_DEFAULT)
             sim2.read_particles(host)
             barrier()

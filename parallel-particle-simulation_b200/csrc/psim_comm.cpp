@@ -15,6 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "psim_internal.h"
 
@@ -33,6 +36,17 @@ struct NcclApi {
 };
 
 static NcclApi g_nccl;
+
+// Communicators are process-level plumbing (the analogue of MPI_COMM_WORLD, which the reference's MPI driver sets up
+// before its timer, part2/main.cpp): a communicator created for a given unique id and slab geometry is kept for the life
+// of the process and shared by every handle that connects with the same id, so that a second simulation does not pay the
+// NCCL bootstrap (about a second) again.
+struct CachedComm {
+    std::string key;
+    ncclComm_t comm;
+};
+static std::vector<CachedComm> g_comms;
+static std::mutex g_comms_mutex;
 
 static int load_nccl() {
     if (g_nccl.lib) return PSIM_OK;
@@ -218,8 +232,7 @@ void comm_destroy(psim_sim* sim) {
         sim->ev_b[k] = sim->ev_i[k] = nullptr;
     }
     sim->p2p = false;
-    if (sim->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(sim->comm));
-    sim->comm = nullptr;
+    sim->comm = nullptr;   // the communicator itself stays cached for the process (see g_comms)
     if (sim->ev_boundary) cudaEventDestroy(sim->ev_boundary);
     if (sim->ev_exchanged) cudaEventDestroy(sim->ev_exchanged);
     if (sim->comm_stream) cudaStreamDestroy(sim->comm_stream);
@@ -250,7 +263,17 @@ extern "C" int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]) 
     ncclUniqueId id;
     std::memcpy(&id, id128, 128);
     ncclComm_t comm = nullptr;
-    PSIM_NCCL(g_nccl.CommInitRank(&comm, sim->nranks, id, sim->rank));
+    {
+        std::lock_guard<std::mutex> lock(g_comms_mutex);
+        std::string key(reinterpret_cast<const char*>(id128), 128);
+        key += "/" + std::to_string(sim->rank) + "/" + std::to_string(sim->nranks) + "/" + std::to_string(sim->device);
+        for (const CachedComm& c : g_comms)
+            if (c.key == key) comm = c.comm;
+        if (!comm) {
+            PSIM_NCCL(g_nccl.CommInitRank(&comm, sim->nranks, id, sim->rank));
+            g_comms.push_back({key, comm});
+        }
+    }
     sim->comm = comm;
     int lo = 0, hi = 0;
     PSIM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
