@@ -11,30 +11,35 @@
 // scan or scatter in the time loop.
 //
 // Per step one persistent kernel (tile_step_kernel); a CTA walks tiles blockIdx.x, +gridDim.x, ...
-// A producer warp runs two tiles ahead and feeds a two-stage shared-memory pipeline with TMA bulk
-// copies (cp.async.bulk + mbarrier): the tile's three stripes, the eight neighbour halo lists (landing
-// directly behind the own particles as the "apron") and the nine surrounding outboxes.  The consumer
-// warps then do, with four CTA barriers per tile:
-//   A. ingest + bin: particles that entered the tile last step (outbox records of the 3x3 tiles) are
-//      appended; own and apron particles are binned into a (TS+2)^2 cell table IN SHARED MEMORY --
-//      per cell the head of a linked list (one atomicExch per particle; reference part3/gpu.cu:92-112
-//      does this in global memory with 16 fixed slots per cell) and one bit in a per-row occupancy map
+// Seven consumer warps plus one PRODUCER warp that sleeps in the hardware barriers the consumers pass anyway:
+//   producer, one tile ahead: list counts fetched early, then TMA bulk copies (cp.async.bulk + mbarrier) into the
+//      other shared-memory stage -- the tile's three stripes, the eight neighbour halo lists (landing directly
+//      behind the own particles as the one-cell "apron") and the nine surrounding outboxes packed back to back --
+//      then the INGEST: particles that entered the tile last step (outbox records whose destination cell lies
+//      in the tile) are appended to the stripe, records in the apron ring become apron particles, and apron +
+//      migrants + the own slots past the consumers' share are binned.
+//   A. bin (consumers, during the PREVIOUS tile's phase C): every particle that was already in the tile goes
+//      into a (TS+2)^2 cell table IN SHARED MEMORY -- per cell the head of a linked list (one atomicExch per
+//      particle; reference part3/gpu.cu:92-112 does this in global memory with 16 fixed slots per cell) and one
+//      bit in a per-row occupancy map; its position in cell units is kept in FP32.      -- barrier 1 --
 //   B. search: every own particle takes the 9 occupancy bits of its 3x3 neighbourhood (reference
-//      part1/serial.cpp:102-117), walks only the non-empty cells and tests candidates in FP32 on
-//      tile-relative coordinates against a slightly widened cutoff; survivors go to a CTA-wide pair list
-//   C. pair evaluation, dense: one lane per listed pair redoes the distance test in exact FP64 and, if in
-//      range, evaluates the coefficient (sqrt + three divisions, reference part1/serial.cpp:19-36).  The
-//      expensive FP64 sequence runs once per tile with full lanes instead of once per warp with ~3.
-//   D. sum (<= 2 contributions are order independent; more take the canonical-order path), move + reflect
-//      (reference part1/serial.cpp:46-61), new cell, stay / leave decision, warp ballots
-//   E. re-tile: stayers are written to the other stripe buffer compacted by a ballot prefix, leavers go to
-//      the tile's outbox, particles in the tile's boundary cells are appended to the edge / corner halo
-//      lists the neighbours read next step.
+//      part1/serial.cpp:102-117), walks only the non-empty cells and tests candidates in FP32 against a slightly
+//      widened cutoff; survivors go to a CTA-wide pair list.                                -- barrier 2 --
+//   C. pair evaluation, dense (last consumer warp): one lane per listed pair redoes the distance test in exact
+//      FP64 and, if in range, evaluates the coefficient (sqrt + three divisions, reference part1/serial.cpp:19-36):
+//      the expensive sequence runs once per tile with full lanes instead of once per warp with ~3.  Particles with
+//      three or more candidates take the exact canonical-order path here.  The other warps run phase A of the next
+//      tile meanwhile.                                                                      -- barrier 3 --
+//   D+E. sum (<= 2 contributions are order independent), move + reflect (reference part1/serial.cpp:46-61), new
+//      cell, stay / leave; slots come from one warp-aggregated shared atomic per warp, so without a further
+//      barrier stayers are stored compacted into the other stripe buffer, leavers into the tile's outbox and
+//      particles in boundary cells into the edge / corner halo lists the neighbours read next step.
 //
-// Slabs (precedent reference part2/mpi.cpp:258-270,296-365): a rank owns a
-// contiguous range of tile rows plus one ghost tile row on each side that holds only exports.  The
-// exports of one tile row are one contiguous byte range, so the halo exchange AND the particle
-// migration between GPUs are a single send/receive of the first / last owned row per neighbour.
+// Slabs (precedent reference part2/mpi.cpp:258-270,296-365): a rank owns a contiguous range
+// of tile rows plus one ghost tile row on each side that holds only exports.  The exports of one tile row are one
+// contiguous byte range, so the halo exchange AND the particle migration between GPUs are the same data: either one
+// ncclSend/ncclRecv of the first / last owned row per neighbour, or -- the default on one NVSwitch box -- stored by
+// the boundary-row launch straight into the neighbour's ghost row over NVLink (tiled_step).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
