@@ -8,7 +8,9 @@
  * exact in one FMA, and 100.0 == RN(1 / 0.01)).  This program compares the two on
  *   1. every double within 200 ulps of every cell edge k * 0.01, k = 0 .. 40000  (16 M values),
  *   2. N random positions in [0, 400)                                              (argv[1], default 2e9),
- *   3. a few special values,
+ *   3. N/4 magnitudes spread log-uniformly over 1e-12 .. 2e12 with both signs (the force coefficient is divided by
+ *      mass == 0.01 as well),
+ *   4. a few special values,
  * and exits non-zero on any mismatch other than the sign of a zero quotient.
  *
  * Build: gcc -O2 -ffp-contract=off -o check_div check_div.c -lm   (fma() from libm is exact with or without hardware FMA)
@@ -47,6 +49,14 @@ int main(int argc, char **argv) {
         for (int j = 0; j < 400; ++j) { n += check(x, &bad); x = nextafter(x, 1e9); }
     }
     for (long i = 0; i < nrand; ++i) n += check((double)(rnd() >> 11) * (1.0 / 9007199254740992.0) * 400.0, &bad);
+    /* 4. the force coefficient is also divided by mass == 0.01 (reference part1/serial.cpp:33): magnitudes up to 1e10, both signs */
+    for (long i = 0; i < nrand / 4; ++i) {
+        const double u = (double)(rnd() >> 11) * (1.0 / 9007199254740992.0);
+        const double v = (double)(rnd() >> 11) * (1.0 / 9007199254740992.0);
+        const double x = (1.0 + v) * pow(10.0, -12.0 + 24.0 * u);
+        n += check(x, &bad);
+        n += check(-x, &bad);
+    }
     const double sp[] = {0.0, -0.0, 1e-300, 1e-310, 4.9e-324, 1e-20, 0.01, 0.02, 100.0, 282.84271247461902, 399.99999999999994};
     for (unsigned i = 0; i < sizeof sp / sizeof *sp; ++i) n += check(sp[i], &bad);
     printf("checked %ld values, %ld mismatches\n", n, bad);

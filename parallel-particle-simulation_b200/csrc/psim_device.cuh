@@ -62,7 +62,10 @@ __device__ __forceinline__ double pair_r2(double dx, double dy) {
 __device__ __forceinline__ void pair_contrib(double dx, double dy, double r2, double& cx, double& cy) {
     r2 = fmax(r2, kMinR2);
     const double r = __dsqrt_rn(r2);
-    const double coef = __ddiv_rn(__ddiv_rn(__dsub_rn(1.0, __ddiv_rn(kCutoff, r)), r2), kMass);
+    // the last division is by mass == 0.01: the same exact two-FMA quotient as the cell index (oracle/check_div.c also
+    // sweeps the coefficient's range, both signs); a zero quotient may differ in sign only, which a sum from +0 absorbs
+    static_assert(PSIM_MASS == PSIM_BIN_SIZE, "div_by_bin divides by 0.01");
+    const double coef = div_by_bin(__ddiv_rn(__dsub_rn(1.0, __ddiv_rn(kCutoff, r)), r2));
     cx = __dmul_rn(coef, dx);
     cy = __dmul_rn(coef, dy);
 }
