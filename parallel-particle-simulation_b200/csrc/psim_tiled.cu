@@ -309,27 +309,25 @@ __device__ __forceinline__ void issue_tile(const TileParams& P, const TileCoord 
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
     const int cj = lane < 18 ? clamp_count<TS>(cj_raw, lane) : 0;
-    // exclusive prefixes: halo entries over lanes 1..8, staged outbox records over lanes 9..17
+    // exclusive prefixes in ONE scan: halo entries over lanes 1..8 (low 16 bits), outbox records over lanes 9..17 (high)
     const int hv = (lane >= 1 && lane <= 8) ? cj : 0;
     const int ov = (lane >= 9 && lane <= 17) ? cj : 0;
-    int hs = hv, os = ov;
+    int scan = hv | (ov << 16);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, hs, o), b = __shfl_up_sync(0xffffffffu, os, o);
-        if (lane >= o) {
-            hs += a;
-            os += b;
-        }
+        const int a = __shfl_up_sync(0xffffffffu, scan, o);
+        if (lane >= o) scan += a;
     }
-    const int n_halo = __shfl_sync(0xffffffffu, hs, 8), n_staged = min(__shfl_sync(0xffffffffu, os, 17), D::OS);
+    const int hs = scan & 0xFFFF, os = scan >> 16;
+    const int totals = __shfl_sync(0xffffffffu, scan, 17);
+    const int n_halo = totals & 0xFFFF, n_staged = min(totals >> 16, D::OS);
     const int staged = max(0, min(ov, D::OS - (os - ov)));   // lanes 9..17: records of my outbox that fit the staging area
     const int n = __shfl_sync(0xffffffffu, cj, 0);
-    // what this lane copies
-    const int src_lane = lane < 3 ? 0 : lane < 11 ? lane - 2 : lane < 20 ? lane - 2 : 0;   // lane holding the count of my copy
-    const int my_cnt = __shfl_sync(0xffffffffu, cj, src_lane);
-    const int my_hoff = __shfl_sync(0xffffffffu, hs - hv, src_lane);
-    const int my_ooff = __shfl_sync(0xffffffffu, os - ov, src_lane);
-    const int my_staged = __shfl_sync(0xffffffffu, staged, src_lane);
+    // what this lane copies: count, destination offset and staged records of "its" list, fetched from the lane that holds them
+    const int src_lane = lane < 3 ? 0 : lane < 20 ? lane - 2 : 0;
+    const int mine = __shfl_sync(0xffffffffu, cj | (staged << 16), src_lane);
+    const int offs = __shfl_sync(0xffffffffu, (hs - hv) | ((os - ov) << 16), src_lane);
+    const int my_cnt = mine & 0xFFFF, my_staged = mine >> 16, my_hoff = offs & 0xFFFF, my_ooff = offs >> 16;
     if (lane < 18) cnt[lane] = cj;
     if (lane == 18) cnt[18] = n_halo;
     if (lane == 19) cnt[19] = n_staged;
@@ -362,9 +360,10 @@ __device__ __forceinline__ void issue_tile(const TileParams& P, const TileCoord 
             dst = st.obox + my_ooff;
         }
     }
-    unsigned total = bytes;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    // bytes in flight for this tile, known without a reduction: two 16-byte stripes, the id stripe rounded up to 16 bytes, the
+    // halo entries and the staged outbox records
+    const unsigned total = (unsigned)n * 32u + (unsigned)((n + 3) >> 2) * 16u + (unsigned)n_halo * 16u +
+                           (unsigned)n_staged * (unsigned)sizeof(OutRec);
     __syncwarp();   // counts are in shared memory before the barrier can complete
     if (lane == 0) mbar_arrive_expect_tx(bar, total);
     __syncwarp();
