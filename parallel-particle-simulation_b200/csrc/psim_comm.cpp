@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -68,6 +69,7 @@ static int load_nccl() {
     PSIM_SYM(Recv, "ncclRecv")
     PSIM_SYM(GroupStart, "ncclGroupStart")
     PSIM_SYM(GroupEnd, "ncclGroupEnd")
+    PSIM_SYM(AllReduce, "ncclAllReduce")
     PSIM_SYM(GetErrorString, "ncclGetErrorString")
 #undef PSIM_SYM
     g_nccl.lib = lib;
@@ -157,19 +159,43 @@ static int p2p_setup(psim_sim* sim, ncclComm_t comm) {
     PSIM_CUDA(cudaStreamSynchronize(s));
     PSIM_CUDA(cudaMemcpy(theirs, d_buf + 1, 2 * sizeof(P2PHandles), cudaMemcpyDeviceToHost));
     cudaFree(d_buf);
-    for (int side = 0; side < 2; ++side) {
+    // map the neighbours' buffers; the outcome is agreed on by ALL slabs (min over ranks), so that either every rank uses the
+    // peer-memory exchange or every rank stays on NCCL send / recv -- a one-sided failure must not leave a neighbour waiting
+    int ok = 1;
+    for (int side = 0; side < 2 && ok; ++side) {
         const bool have = side == 0 ? sim->rank > 0 : sim->rank < sim->nranks - 1;
         if (!have) continue;
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 2 && ok; ++b) {
             void* p = nullptr;
-            cudaError_t e = cudaIpcOpenMemHandle(&p, theirs[side].exports[b], cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) return fail(PSIM_ERR_COMM, "cudaIpcOpenMemHandle(neighbour exports): %s", cudaGetErrorString(e));
-            sim->peer_exports[side][b] = static_cast<char*>(p);
+            if (cudaIpcOpenMemHandle(&p, theirs[side].exports[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+            else sim->peer_exports[side][b] = static_cast<char*>(p);
         }
         void* f = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&f, theirs[side].flags, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) return fail(PSIM_ERR_COMM, "cudaIpcOpenMemHandle(neighbour flags): %s", cudaGetErrorString(e));
-        sim->peer_flags[side] = static_cast<int*>(f);
+        if (ok && cudaIpcOpenMemHandle(&f, theirs[side].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+        else if (ok) sim->peer_flags[side] = static_cast<int*>(f);
+    }
+    if (!ok) cudaGetLastError();
+    {
+        int* d_ok = nullptr;
+        PSIM_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+        PSIM_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+        PSIM_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, comm, s));
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        PSIM_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d_ok);
+    }
+    if (!ok) {   // somebody could not map a neighbour: everybody keeps the NCCL flavour
+        for (int side = 0; side < 2; ++side) {
+            for (int b = 0; b < 2; ++b) {
+                if (sim->peer_exports[side][b]) cudaIpcCloseMemHandle(sim->peer_exports[side][b]);
+                sim->peer_exports[side][b] = nullptr;
+            }
+            if (sim->peer_flags[side]) cudaIpcCloseMemHandle(sim->peer_flags[side]);
+            sim->peer_flags[side] = nullptr;
+        }
+        cudaFree(sim->d_flags);
+        sim->d_flags = nullptr;
+        return PSIM_OK;
     }
     for (int k = 0; k < 2; ++k) {
         PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_b[k], cudaEventDisableTiming));
