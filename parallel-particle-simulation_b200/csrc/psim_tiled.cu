@@ -303,9 +303,13 @@ __device__ __forceinline__ int load_count(const TileParams& P, const TileCoord& 
 // global-load latency is hidden), publish them in `cnt` and issue the bulk copies into `st`.
 //   copy 0 pos, 1 vel, 2 id, 3..10 apron source k = copy-3 (straight to its final place behind the own
 //   particles), 11..19 outbox nb = copy-11 (first CS records, packed back to back)
+struct TileCopy {   // what one producer lane copies for a tile: prepared one tile early, fired the moment the stage is free
+    const void* src;
+    void* dst;
+    unsigned bytes, total;
+};
 template <int TS>
-__device__ __forceinline__ void issue_tile(const TileParams& P, const TileCoord c, Stage<TS>& st, int* cnt, unsigned long long* bar,
-                                           int cj_raw, int lane) {
+__device__ __forceinline__ TileCopy prepare_tile(const TileParams& P, const TileCoord c, Stage<TS>& st, int* cnt, int cj_raw, int lane) {
     using C = TileCfg<TS>;
     using D = TileDims<TS>;
     const int cj = lane < 18 ? clamp_count<TS>(cj_raw, lane) : 0;
@@ -364,10 +368,18 @@ __device__ __forceinline__ void issue_tile(const TileParams& P, const TileCoord 
     // halo entries and the staged outbox records
     const unsigned total = (unsigned)n * 32u + (unsigned)((n + 3) >> 2) * 16u + (unsigned)n_halo * 16u +
                            (unsigned)n_staged * (unsigned)sizeof(OutRec);
+    TileCopy k;
+    k.src = src;
+    k.dst = dst;
+    k.bytes = bytes;
+    k.total = total;
+    return k;
+}
+__device__ __forceinline__ void fire_tile(const TileCopy& k, unsigned long long* bar, int lane) {
     __syncwarp();   // counts are in shared memory before the barrier can complete
-    if (lane == 0) mbar_arrive_expect_tx(bar, total);
+    if (lane == 0) mbar_arrive_expect_tx(bar, k.total);
     __syncwarp();
-    if (bytes) tma_load_1d(dst, src, bytes, bar);
+    if (k.bytes) tma_load_1d(k.dst, k.src, k.bytes, bar);
 }
 
 // Rare path: exact FP64 walk of the 3x3 neighbourhood with canonical-order summation (particles whose
@@ -575,8 +587,16 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             __syncwarp();
         };
 
-        issue_tile<TS>(P, walk.coord(P), S.st[0], S.cnts[0], &S.full[0], lane < 18 ? load_count<TS>(P, walk.coord(P), lane) : 0, lane);
-        ingest(0, walk.coord(P), 0u);
+        // The copies of a tile are PREPARED (list counts, offsets, addresses, byte total) one tile before they are FIRED, so
+        // that the bulk copies start the moment barrier 1 frees the stage: their latency, not the producer's arithmetic,
+        // then decides when the consumers can bin the next tile.
+        const TileCoord c0 = walk.coord(P);
+        fire_tile(prepare_tile<TS>(P, c0, S.st[0], S.cnts[0], lane < 18 ? load_count<TS>(P, c0, lane) : 0, lane), &S.full[0], lane);
+        walk.advance(P);   // -> tile 1
+        TileCopy next_copy{nullptr, nullptr, 0u, 0u};
+        if (first + G < P.ntiles)
+            next_copy = prepare_tile<TS>(P, walk.coord(P), S.st[1], S.cnts[1], lane < 18 ? load_count<TS>(P, walk.coord(P), lane) : 0, lane);
+        ingest(0, c0, 0u);
 #ifdef PSIM_PHASE_TIMERS
         unsigned tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         unsigned tlast = (unsigned)clock();
@@ -585,15 +605,19 @@ __global__ void __launch_bounds__(TileCfg<TS>::THREADS + 32, TileCfg<TS>::CTAS) 
             const int t = first + it * G;
             if (t >= P.ntiles) break;
             const int sb = it & 1;
-            const bool has_next = t + G < P.ntiles;
-            walk.advance(P);   // -> tile it + 1
-            const TileCoord cn = walk.coord(P);
-            int cj_next = 0;
-            if (has_next && lane < 18) cj_next = load_count<TS>(P, cn, lane);   // in flight across the barrier
+            const bool has_next = t + G < P.ntiles, has_next2 = t + 2 * G < P.ntiles;
+            const TileCoord cn = walk.coord(P);   // tile it + 1
+            walk.advance(P);                      // -> tile it + 2
+            const TileCoord cn2 = walk.coord(P);
+            int cj2 = 0;
+            if (has_next2 && lane < 18) cj2 = load_count<TS>(P, cn2, lane);   // in flight across the barrier
             PSIM_TICK(0);
             named_sync<kBarTable, T + 32>();   // every consumer warp has left tile it - 1: its stage is free
             PSIM_TICK(1);
-            if (has_next) issue_tile<TS>(P, cn, S.st[sb ^ 1], S.cnts[sb ^ 1], &S.full[sb ^ 1], cj_next, lane);
+            if (has_next) fire_tile(next_copy, &S.full[sb ^ 1], lane);
+            // tile it + 2 will use THIS tile's stage: only its addresses and count words are set up now (nobody reads the count
+            // words of a tile once it is binned and ingested), the copies are fired after the next barrier 1
+            if (has_next2) next_copy = prepare_tile<TS>(P, cn2, S.st[sb], S.cnts[sb], cj2, lane);
             PSIM_TICK(2);
             named_sync<kBarForces, T + 32>();  // the consumers have cleaned the other cell table and are done with rel / pcell
             PSIM_TICK(3);
