@@ -48,11 +48,15 @@ extern "C" {
 #define PSIM_ERR_UNSUPPORTED  7  /* configuration the selected engine cannot run                */
 
 /* ---- engines ---- */
-#define PSIM_ENGINE_AUTO      0  /* tiled when the particle density fits its tiles, else cellsort */
+#define PSIM_ENGINE_AUTO      0  /* kstep when the particle density fits its tiles, else cellsort */
 #define PSIM_ENGINE_CELLSORT  1  /* per step: atomic histogram over cutoff cells, single-pass
                                     exclusive scan, scatter into cell-sorted SoA, force+move     */
 #define PSIM_ENGINE_TILED     2  /* persistent tile-resident SoA; one fused kernel per step does
                                     in-shared-memory binning, force, move, re-tiling, halo export */
+#define PSIM_ENGINE_KSTEP     3  /* persistent tile-resident SoA; one kernel advances a tile and its
+                                    5-cell halo K (<= 4) steps in shared memory -- binning, force,
+                                    move every step -- and re-tiles once per launch; results are
+                                    bit-identical to stepping one step at a time                    */
 
 /* flags for psim_step */
 #define PSIM_STEP_DEFAULT     0  /* accelerations are materialised for the LAST step of the batch */
@@ -65,7 +69,7 @@ typedef struct psim_config {
     int   engine;        /* PSIM_ENGINE_*                                                        */
     int   device;        /* CUDA device ordinal; -1 = the calling thread's current device        */
     void* stream;        /* cudaStream_t to run on; NULL = a private non-blocking stream         */
-    int   tile_cells;    /* tiled engine: cutoff cells per tile side (16, 32 or 64); 0 = auto    */
+    int   tile_cells;    /* tiled / kstep engines: cutoff cells per tile side (16, 32 or 64); 0 = auto */
     int   use_graph;     /* reserved (ignored): steps are enqueued as plain launches, one per step */
     /* 1-D slab decomposition.  nranks == 1: the whole box.               */
     int   rank;          /* this slab's index along x (cell rows)                                */
@@ -102,6 +106,13 @@ typedef struct psim_info_t {
     int hw_leavers, hw_halo_list, hw_tile_population, hw_apron;
     int outbox_capacity, halo_list_capacity;
     int reserved_hw_pairs;  /* tiled engine: most candidate pairs one tile listed in a step (capacity is internal) */
+    /* kstep engine */
+    int halo_cells;        /* halo width H in cutoff cells                                       */
+    int steps_per_launch;  /* K: time steps fused per kernel launch (PSIM_KSTEPS, default 4)     */
+    int region_capacity;   /* particles of one tile + halo region the kernel can hold            */
+    int recoveries;        /* batches replayed one step per launch after a speed-bound violation  */
+    int engine_switches;   /* kstep -> cellsort hand-overs (stripe / region overflow, or a particle faster than
+                              the one-step halo bound): the handle keeps running on the cellsort engine */
 } psim_info_t;
 
 /* ---- errors ---- */

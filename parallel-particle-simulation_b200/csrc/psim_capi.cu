@@ -187,6 +187,9 @@ static int view_of(psim_sim* sim, SoAView* v, bool* have_acc) {
     if (sim->engine == PSIM_ENGINE_CELLSORT) {
         PSIM_TRY(cellsort_view(sim, v));
         *have_acc = true;
+    } else if (sim->engine == PSIM_ENGINE_KSTEP) {
+        PSIM_TRY(kstep_view(sim, v));
+        *have_acc = true;  // zeros are substituted when the stored accelerations are stale
     } else {
         PSIM_TRY(tiled_view(sim, v));
         *have_acc = true;  // the gather already substitutes zeros when accelerations are stale
@@ -194,9 +197,61 @@ static int view_of(psim_sim* sim, SoAView* v, bool* have_acc) {
     return PSIM_OK;
 }
 
+static int engine_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy);
+
+// kstep -> cellsort hand-over (see check_device_error): the kstep state (rewound to the last good launch) is written out in
+// original order, the cellsort engine is built from it and runs the steps the failed launches still owed.
+static int switch_to_cellsort(psim_sim* sim, int pending_steps, bool store_last) {
+    cudaStream_t s = sim->stream;
+    DeviceArena tmp;
+    particle_t* aos = nullptr;
+    PSIM_TRY(tmp.alloc(&aos, (size_t)std::max(sim->n_total, 1)));
+    int st = kstep_writeback(sim, aos, nullptr);
+    if (st == PSIM_OK && cudaStreamSynchronize(s) != cudaSuccess) st = fail(PSIM_ERR_CUDA, "engine hand-over: %s", cudaGetErrorString(cudaGetLastError()));
+    if (st == PSIM_OK) {
+        kstep_destroy(sim);
+        if (cudaMemsetAsync(sim->d_err, 0, kErrWords * sizeof(int), s) != cudaSuccess) st = fail(PSIM_ERR_CUDA, "engine hand-over: memset");
+    }
+    if (st == PSIM_OK) st = cellsort_create(sim, aos, sim->n_total);
+    if (st == PSIM_OK && cudaStreamSynchronize(s) != cudaSuccess) st = fail(PSIM_ERR_CUDA, "engine hand-over: %s", cudaGetErrorString(cudaGetLastError()));
+    tmp.release();
+    PSIM_TRY(st);
+    sim->engine = PSIM_ENGINE_CELLSORT;
+    ++sim->engine_switches;
+    if (pending_steps > 0) PSIM_TRY(cellsort_step(sim, pending_steps, store_last ? PSIM_STEP_DEFAULT : PSIM_STEP_ACCEL_NONE));
+    PSIM_CUDA(cudaMemcpyAsync(sim->h_err, sim->d_err, kErrWords * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PSIM_CUDA(cudaStreamSynchronize(s));
+    return PSIM_OK;
+}
+
 static int check_device_error(psim_sim* sim) {
-    PSIM_CUDA(cudaMemcpyAsync(sim->h_err, sim->d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
-    PSIM_CUDA(cudaStreamSynchronize(sim->stream));
+    for (int attempt = 0;; ++attempt) {
+        PSIM_CUDA(cudaMemcpyAsync(sim->h_err, sim->d_err, kErrWords * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+        PSIM_CUDA(cudaStreamSynchronize(sim->stream));
+        if (sim->engine != PSIM_ENGINE_KSTEP || !sim->kstep) break;
+        // kstep engine: a launch that exceeded its speed bound left its input untouched and is replayed one step per launch
+        bool replayed = false, pending_store = false;
+        int pending_steps = -1;
+        const int st = kstep_after_sync(sim, &replayed, &pending_steps, &pending_store);
+        if (st != PSIM_OK && pending_steps >= 0 && sim->nranks == 1) {
+            // Not recoverable inside the kstep engine (a stripe or region overflowed, or a particle is faster than even the
+            // one-step halo allows), but the input of the failed launch is intact: hand the state to the cellsort engine,
+            // which has no capacities and no speed limit, and run the steps that are still owed there.
+            PSIM_TRY(switch_to_cellsort(sim, pending_steps, pending_store));
+            break;
+        }
+        if (st != PSIM_OK) {
+            const int e = sim->h_err[0];
+            return fail(st,
+                        "kstep engine: launch %d failed with device flags 0x%x:%s%s%s (high-water marks: stripe %d, region %d); the "
+                        "state was rewound to the input of that launch (step %lld)",
+                        sim->h_err[8] - 1, e, (e & kErrTileOverflow) ? " stripe-overflow" : "",
+                        (e & kErrSmemOverflow) ? " region-overflow" : "", (e & kErrSpeedBound) ? " speed-bound" : "", sim->h_err[3],
+                        sim->h_err[4], sim->steps_done);
+        }
+        if (!replayed) return PSIM_OK;
+        if (attempt > 64) return fail(PSIM_ERR_STATE, "kstep engine: replay does not converge");
+    }
     const int e = *sim->h_err;
     if (sim->h_err[5]) return fail(PSIM_ERR_STATE, "debug guard 0x%x tripped (last tile %d, flags 0x%x)", sim->h_err[5], sim->h_err[6], e);
     if (e == 0) return PSIM_OK;
@@ -222,6 +277,10 @@ static int ensure_scratch(psim_sim* sim, size_t bytes, void** out) {
     }
     *out = sim->scratch_ptr;
     return PSIM_OK;
+}
+
+static int engine_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy) {
+    return sim->engine == PSIM_ENGINE_KSTEP ? kstep_writeback(sim, d_out, d_xy) : tiled_writeback(sim, d_out, d_xy);
 }
 
 struct DeviceGuard {
@@ -347,27 +406,42 @@ int psim_create(psim_sim** out, const psim_config* cfg_in, const particle_t* par
         if (e != cudaSuccess) return bail(fail(PSIM_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
         sim->own_stream = true;
     }
-    int st = sim->mem.alloc(&sim->d_err, 8);
+    int st = sim->mem.alloc(&sim->d_err, kErrWords);
     if (st) return bail(st);
-    if (cudaMemsetAsync(sim->d_err, 0, 8 * sizeof(int), sim->stream) != cudaSuccess ||
-        cudaHostAlloc(&sim->h_err, 8 * sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+    if (cudaMemsetAsync(sim->d_err, 0, kErrWords * sizeof(int), sim->stream) != cudaSuccess ||
+        cudaHostAlloc(&sim->h_err, kErrWords * sizeof(int), cudaHostAllocDefault) != cudaSuccess)
         return bail(fail(PSIM_ERR_CUDA, "psim_create: error-word allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
 
     const bool on_device = num_parts > 0 && pointer_on_device(parts);
     int engine = cfg.engine;
-    if (engine != PSIM_ENGINE_AUTO && engine != PSIM_ENGINE_CELLSORT && engine != PSIM_ENGINE_TILED)
+    if (engine != PSIM_ENGINE_AUTO && engine != PSIM_ENGINE_CELLSORT && engine != PSIM_ENGINE_TILED && engine != PSIM_ENGINE_KSTEP)
         return bail(fail(PSIM_ERR_INVALID, "psim_create: unknown engine %d", engine));
     if (engine == PSIM_ENGINE_CELLSORT && cfg.nranks > 1)
-        return bail(fail(PSIM_ERR_UNSUPPORTED, "psim_create: slabs need the tiled engine"));
+        return bail(fail(PSIM_ERR_UNSUPPORTED, "psim_create: slabs need the kstep or the tiled engine"));
+    if (engine == PSIM_ENGINE_AUTO) {
+        if (const char* pref = std::getenv("PSIM_AUTO_ENGINE")) {   // A/B knob: what AUTO resolves to first
+            if (!std::strcmp(pref, "tiled")) engine = PSIM_ENGINE_TILED;
+            else if (!std::strcmp(pref, "cellsort") && cfg.nranks == 1) engine = PSIM_ENGINE_CELLSORT;
+        }
+    }
 
-    if (engine == PSIM_ENGINE_AUTO || engine == PSIM_ENGINE_TILED) {
+    if (engine == PSIM_ENGINE_AUTO || engine == PSIM_ENGINE_KSTEP) {
+        bool unsuitable = false;
+        st = kstep_create(sim, &cfg, parts, num_parts, on_device, &unsuitable);
+        if (st == PSIM_OK) {
+            sim->engine = PSIM_ENGINE_KSTEP;
+        } else if (unsuitable && engine == PSIM_ENGINE_AUTO && cfg.nranks == 1) {
+            kstep_destroy(sim);
+            engine = PSIM_ENGINE_CELLSORT;
+        } else {
+            return bail(st);
+        }
+    }
+    if (engine == PSIM_ENGINE_TILED) {
         bool unsuitable = false;
         st = tiled_create(sim, &cfg, parts, num_parts, on_device, &unsuitable);
         if (st == PSIM_OK) {
             sim->engine = PSIM_ENGINE_TILED;
-        } else if (unsuitable && engine == PSIM_ENGINE_AUTO && cfg.nranks == 1) {
-            tiled_destroy(sim);
-            engine = PSIM_ENGINE_CELLSORT;
         } else {
             return bail(st);
         }
@@ -405,6 +479,7 @@ int psim_destroy(psim_sim* sim) {
     comm_destroy(sim);
     cellsort_destroy(sim);
     tiled_destroy(sim);
+    kstep_destroy(sim);
     sim->scratch.release();
     sim->mem.release();
     if (sim->h_err) cudaFreeHost(sim->h_err);
@@ -418,6 +493,7 @@ int psim_step(psim_sim* sim, int nsteps, int flags) {
     if (nsteps < 0) return fail(PSIM_ERR_INVALID, "psim_step: nsteps %d", nsteps);
     if (nsteps == 0) return PSIM_OK;
     DeviceGuard g(sim->device);
+    if (sim->engine == PSIM_ENGINE_KSTEP) return kstep_step(sim, nsteps, flags);
     return sim->engine == PSIM_ENGINE_CELLSORT ? cellsort_step(sim, nsteps, flags) : tiled_step(sim, nsteps, flags);
 }
 
@@ -431,17 +507,17 @@ int psim_read_particles(psim_sim* sim, particle_t* dst) {
     if (!sim || !dst) return fail(PSIM_ERR_INVALID, "psim_read_particles: NULL argument");
     DeviceGuard g(sim->device);
     PSIM_TRY(check_device_error(sim));
-    if (sim->engine == PSIM_ENGINE_TILED && sim->nranks == 1) {
+    if ((sim->engine == PSIM_ENGINE_TILED || sim->engine == PSIM_ENGINE_KSTEP) && sim->nranks == 1) {
         // one pass straight from the tiles into the caller's order (no intermediate compaction)
         cudaStream_t s = sim->stream;
         if (pointer_on_device(dst)) {
-            PSIM_TRY(tiled_writeback(sim, dst, nullptr));
+            PSIM_TRY(engine_writeback(sim, dst, nullptr));
             PSIM_CUDA(cudaStreamSynchronize(s));
             return PSIM_OK;
         }
         particle_t* stage = nullptr;
         PSIM_TRY(ensure_scratch(sim, sizeof(particle_t) * (size_t)std::max(sim->n_total, 1), reinterpret_cast<void**>(&stage)));
-        PSIM_TRY(tiled_writeback(sim, stage, nullptr));
+        PSIM_TRY(engine_writeback(sim, stage, nullptr));
         PSIM_CUDA(cudaMemcpyAsync(dst, stage, sizeof(particle_t) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
         PSIM_CUDA(cudaStreamSynchronize(s));
         return PSIM_OK;
@@ -485,16 +561,16 @@ int psim_read_positions(psim_sim* sim, double* xy) {
     if (!sim || !xy) return fail(PSIM_ERR_INVALID, "psim_read_positions: NULL argument");
     DeviceGuard g(sim->device);
     PSIM_TRY(check_device_error(sim));
-    if (sim->engine == PSIM_ENGINE_TILED && sim->nranks == 1) {
+    if ((sim->engine == PSIM_ENGINE_TILED || sim->engine == PSIM_ENGINE_KSTEP) && sim->nranks == 1) {
         cudaStream_t s = sim->stream;
         if (pointer_on_device(xy)) {
-            PSIM_TRY(tiled_writeback(sim, nullptr, reinterpret_cast<double2*>(xy)));
+            PSIM_TRY(engine_writeback(sim, nullptr, reinterpret_cast<double2*>(xy)));
             PSIM_CUDA(cudaStreamSynchronize(s));
             return PSIM_OK;
         }
         double2* stage = nullptr;
         PSIM_TRY(ensure_scratch(sim, sizeof(double2) * (size_t)std::max(sim->n_total, 1), reinterpret_cast<void**>(&stage)));
-        PSIM_TRY(tiled_writeback(sim, nullptr, stage));
+        PSIM_TRY(engine_writeback(sim, nullptr, stage));
         PSIM_CUDA(cudaMemcpyAsync(xy, stage, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
         PSIM_CUDA(cudaStreamSynchronize(s));
         return PSIM_OK;
@@ -655,7 +731,14 @@ int psim_info(psim_sim* sim, psim_info_t* out) {
     out->steps_done = sim->steps_done;
     out->kernel_launches = sim->launches;
     out->num_parts = sim->n_total;
-    out->device_bytes = (long long)sim->mem.bytes + cellsort_bytes(sim) + tiled_bytes(sim);
+    out->engine_switches = sim->engine_switches;
+    out->device_bytes = (long long)sim->mem.bytes + cellsort_bytes(sim) + tiled_bytes(sim) + kstep_bytes(sim);
+    if (sim->engine == PSIM_ENGINE_KSTEP) {
+        kstep_info(sim, out);
+        out->hw_tile_population = sim->h_err[3];
+        out->hw_apron = sim->h_err[4];
+        out->reserved_hw_pairs = sim->h_err[7];
+    }
     if (sim->engine == PSIM_ENGINE_TILED) {
         tiled_info(sim, out);
         out->hw_leavers = sim->h_err[1];

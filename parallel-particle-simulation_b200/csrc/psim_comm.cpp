@@ -104,6 +104,34 @@ int tiled_exchange(psim_sim* sim, int parity, cudaStream_t s) {
     return PSIM_OK;
 }
 
+// kstep engine: a tile row is four byte ranges (headers, pos, vel, id stripes); the first / last owned row goes to the
+// neighbour's ghost row.  Used for the first exchange after create and, per launch, by the NCCL flavour.
+int kstep_exchange(psim_sim* sim, int parity, cudaStream_t s) {
+    if (sim->nranks == 1) return PSIM_OK;
+    if (!sim->comm) return fail(PSIM_ERR_STATE, "slab %d/%d is not connected: call psim_comm_connect first", sim->rank, sim->nranks);
+    ncclComm_t comm = static_cast<ncclComm_t>(sim->comm);
+    const int lrows = kstep_owned_rows(sim);
+    char *first[4], *last[4], *glo[4], *ghi[4];
+    size_t bytes[4];
+    kstep_row_ranges(sim, parity, 1, first, bytes);
+    kstep_row_ranges(sim, parity, lrows, last, bytes);
+    kstep_row_ranges(sim, parity, 0, glo, bytes);
+    kstep_row_ranges(sim, parity, lrows + 1, ghi, bytes);
+    PSIM_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < 4; ++k) {
+        if (sim->rank > 0) {
+            PSIM_NCCL(g_nccl.Send(first[k], bytes[k], ncclInt8, sim->rank - 1, comm, s));
+            PSIM_NCCL(g_nccl.Recv(glo[k], bytes[k], ncclInt8, sim->rank - 1, comm, s));
+        }
+        if (sim->rank < sim->nranks - 1) {
+            PSIM_NCCL(g_nccl.Send(last[k], bytes[k], ncclInt8, sim->rank + 1, comm, s));
+            PSIM_NCCL(g_nccl.Recv(ghi[k], bytes[k], ncclInt8, sim->rank + 1, comm, s));
+        }
+    }
+    PSIM_NCCL(g_nccl.GroupEnd());
+    return PSIM_OK;
+}
+
 // ---- peer-memory exchange ----------------------------------------------------------------------------
 // Each slab maps its neighbours' export buffers and flag words (CUDA IPC; the 64-byte handles travel through the
 // NCCL communicator once at connect time).  Per step: the kernel stores its boundary rows' exports into the
@@ -123,9 +151,11 @@ static int p2p_setup(psim_sim* sim, ncclComm_t comm) {
     char *e0, *e1;
     size_t bytes, row_bytes;
     int lrows, ntx;
-    tiled_export_buffers(sim, &e0, &e1, &bytes, &row_bytes, &lrows, &ntx);
+    if (sim->kstep) kstep_shared_buffers(sim, &e0, &e1, &bytes, &ntx);
+    else tiled_export_buffers(sim, &e0, &e1, &bytes, &row_bytes, &lrows, &ntx);
     if (ntx / sim->nranks < 2) return PSIM_OK;   // (same decision on every rank) a one-row slab would have to mirror the same row to both sides: keep NCCL
     (void)lrows;
+    (void)row_bytes;
     if (!g_wait_value32) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -306,6 +336,6 @@ extern "C" int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]) 
     PSIM_CUDA(cudaStreamCreateWithPriority(&sim->comm_stream, cudaStreamNonBlocking, hi));   // exchange first
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_boundary, cudaEventDisableTiming));
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_exchanged, cudaEventDisableTiming));
-    if (sim->tiled) PSIM_TRY(p2p_setup(sim, comm));
+    if (sim->tiled || sim->kstep) PSIM_TRY(p2p_setup(sim, comm));
     return PSIM_OK;
 }

@@ -37,7 +37,9 @@ enum : int {
     kErrOutboxOverflow = 4,   // more particles left a tile in one step than its outbox holds
     kErrSmemOverflow   = 8,   // a tile's working set (own + apron) exceeded the shared-memory staging area
     kErrLostParticle   = 16,  // a particle moved farther than one tile in one step
+    kErrSpeedBound     = 32,  // kstep engine: a velocity exceeded the bound that keeps K fused steps exact (replayed with K = 1)
 };
+constexpr int kErrWords = 16;   // device error block: [0] flags, [1..7] high-water marks / debug, [8] first failed launch + 1
 
 // ---- device buffer bookkeeping ---------------------------------------------------------------
 struct DeviceArena {
@@ -115,6 +117,7 @@ struct CellBinner {
 
 struct CellsortEngine;
 struct TiledEngine;
+struct KstepEngine;
 
 }  // namespace psim
 
@@ -130,11 +133,13 @@ struct psim_sim {
     int row_begin = 0, row_end = 0;
     long long steps_done = 0;
     long long launches = 0;
+    int engine_switches = 0;  // kstep -> cellsort hand-overs after an unrecoverable capacity / speed failure
     int* d_err = nullptr;  // device error word
     int* h_err = nullptr;  // pinned mirror
     psim::DeviceArena mem;
     psim::CellsortEngine* cs = nullptr;
     psim::TiledEngine* tiled = nullptr;
+    psim::KstepEngine* kstep = nullptr;
     // scratch for observation calls
     psim::DeviceArena scratch;
     char* scratch_ptr = nullptr;
@@ -180,5 +185,23 @@ int tiled_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy);  // origin
 void tiled_destroy(psim_sim* sim);
 long long tiled_bytes(psim_sim* sim);
 void tiled_info(psim_sim* sim, psim_info_t* out);
+int tiled_tile_rows(int bincnt, int ts);
+void tiled_slab_rows(int ntx, int rank, int nranks, int* begin, int* end);
+
+// kstep engine (psim_kstep.cu): K steps fused per launch in shared memory
+int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts, int n, bool parts_on_device,
+                 bool* unsuitable);
+int kstep_step(psim_sim* sim, int nsteps, int flags);
+int kstep_after_sync(psim_sim* sim, bool* replayed, int* pending_steps, bool* pending_store);   // error words are in sim->h_err, stream idle
+int kstep_view(psim_sim* sim, SoAView* out);
+int kstep_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy);
+void kstep_destroy(psim_sim* sim);
+long long kstep_bytes(psim_sim* sim);
+void kstep_info(psim_sim* sim, psim_info_t* out);
+int kstep_default_tile(int bincnt);
+int kstep_exchange(psim_sim* sim, int parity, cudaStream_t s);  // psim_comm.cpp
+void kstep_shared_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, int* ntx);
+void kstep_row_ranges(psim_sim* sim, int parity, int lrow, char* ptr[4], size_t bytes[4]);
+int kstep_owned_rows(psim_sim* sim);
 
 }  // namespace psim

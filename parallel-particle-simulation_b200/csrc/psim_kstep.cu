@@ -1,0 +1,1294 @@
+// psim_kstep.cu -- the "kstep" engine: tile-resident particles, K time steps fused per launch in shared memory.
+//
+// Why.  The per-step hot path (bin -> 3x3 force gather -> move, reference part1/serial.cpp:119-131,
+// part3/gpu.cu:187-208) moves 80 bytes per particle-step through HBM but needs a few hundred instructions per
+// particle to find the ~0.1 in-range pairs; on a B200 the instruction issue rate, not HBM, is what binds a
+// one-step-per-launch kernel (ncu: profiles/r1k_*).  Particles move at most ~0.15 cutoff cells per step, so a
+// tile that is loaded together with an H-cell halo can be advanced K steps without looking at HBM again:
+//   * the gather / re-tile / export machinery runs once per K steps instead of once per step,
+//   * HBM traffic per particle-step drops by about K (the kernel stays far from the HBM roofline),
+//   * slabs exchange their boundary bands once per K steps.
+// The redundantly computed halo particles are bit-identical in every tile that computes them (IEEE arithmetic,
+// canonical summation order), so "every tile keeps the particles that END inside it" partitions the particles
+// exactly.
+//
+// Exactness of the halo argument.  Let d be a bound on the displacement of any particle in one step.  A tile
+// loads every particle within H cells of its border (region R0).  Define U_0 = R0 and U_{s+1} = U_s shrunk by
+// (cutoff + d).  Induction over the sub-steps: every loaded particle whose computed position at sub-step s lies in
+// U_s carries its true state, and every particle truly in U_s is loaded (its force partners lie within one cutoff,
+// i.e. inside U_s; a particle that shows up in U_{s+1} was within d of it one step earlier).  With
+// H >= K * (1 + d / cutoff) the tile itself lies in U_K.  d is enforced, not assumed: every computed velocity
+// component is compared with d / dt in every sub-step (all loaded particles, so that no mis-computed halo particle
+// can jump into the trusted region either); a violation raises kErrSpeedBound, later launches become no-ops, and the
+// host replays the batch from the untouched input buffers with K = 1 (d = H - 1 cells; kstep_recover).
+//
+// Layout in HBM.  Tiles of TS x TS cutoff cells; a tile owns a stripe of CAP slots in three streams pos (double2),
+// vel (double2), id (int), double buffered by launch parity, plus acc (double2) for launches that keep the last
+// accelerations.  Inside a stripe the particles are partitioned into nine classes by the H-wide border band their
+// cell lies in, stored in ring order TL T TR R BR B BL L M, and a 16-int header per tile holds the ten prefix
+// offsets.  A neighbour's halo band is then at most two contiguous slot ranges: a tile gathers its region with 10
+// ranges (own stripe, four edge bands -- the E neighbour's left band wraps around the ring and takes two -- and four
+// corners), each one TMA bulk copy (cp.async.bulk -> UBLKCP) for pos and one for vel, completion on an mbarrier.
+//
+// The kernel (kstep_kernel<TS, acc, peer>): persistent CTAs, one tile at a time, T threads:
+//   load     10 ranges -> shared memory (TMA for pos / vel, plain loads for the ids); wipe the cell table
+//   bin      every loaded particle into a (TS+2H+2)^2 cell table in shared memory: per cell the head of a linked list
+//            (reference part3/gpu.cu:92-112 does this in global memory with 16 fixed slots) + one occupancy bit
+//   K times  pass 1  each particle takes the 9 occupancy bits of its 3x3 neighbourhood (reference serial.cpp:102-117),
+//                    walks the non-empty cells, tests candidates in exact FP64 and remembers up to two in-range
+//                    neighbours; in-range pairs go to a per-WARP list
+//            eval    the warp evaluates its listed pairs densely, one lane per pair (sqrt + divisions of
+//                    reference serial.cpp:29-33 run once per warp and sub-step instead of once per particle pass)
+//            pass 2  sum (<= 2 terms are order independent; >= 3 take the canonical-order exact path), move + reflect
+//                    (serial.cpp:46-61), speed check, new cell, insert into the cell table of the NEXT sub-step
+//            one __syncthreads per sub-step: positions, list links and occupancy maps are double buffered by sub-step
+//            parity, the two parities of a cell's list head share one 32-bit word (halves), entries carry the
+//            sub-step number so a table is wiped once per tile only
+//   store    particles whose final cell lies in the tile are ranked inside their class (shared atomics), the class
+//            offsets become the tile's new header, and pos / vel / id (/ acc) are stored to the other parity.  Tiles
+//            of a slab's first / last row also store their facing band straight into the neighbour GPU's ghost row.
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+
+#include "psim_force.cuh"
+#include "psim_internal.h"
+
+namespace psim {
+
+// ------------------------------------------------------------------------------------------
+// compile-time tile configurations
+// ------------------------------------------------------------------------------------------
+// H halo cells, KMAX = H - 1 fused steps, T threads, CTAS resident CTAs per SM, CAP slots per stripe
+// (mean population 0.2 TS^2), NMAX particles of one region (tile + halo) in shared memory.
+template <int TS, int H> struct KCfg;
+template <> struct KCfg<16, 3> { static constexpr int KMAX = 2, T = 64,  CTAS = 8, CAP = 128,  NMAX = 256; };
+template <> struct KCfg<16, 4> { static constexpr int KMAX = 3, T = 64,  CTAS = 8, CAP = 128,  NMAX = 288; };
+template <> struct KCfg<32, 3> { static constexpr int KMAX = 2, T = 128, CTAS = 5, CAP = 352,  NMAX = 480; };
+template <> struct KCfg<32, 4> { static constexpr int KMAX = 3, T = 128, CTAS = 5, CAP = 352,  NMAX = 512; };
+#ifndef PSIM_KSTEP_T64
+#define PSIM_KSTEP_T64 384
+#endif
+template <> struct KCfg<64, 3> { static constexpr int KMAX = 2, T = PSIM_KSTEP_T64, CTAS = 2, CAP = 1024, NMAX = 1216; };
+template <> struct KCfg<64, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T64, CTAS = 2, CAP = 1024, NMAX = 1280; };
+
+constexpr int kHdrInts = 16;          // per tile: ten prefix offsets (ring order TL T TR R BR B BL L M, [9] = population)
+constexpr int kRanges = 10;           // slot ranges that make up a tile's region
+constexpr unsigned kIdxBits = 11;     // list entries: sub-step number << 11 | particle slot in shared memory
+constexpr unsigned kIdxMask = (1u << kIdxBits) - 1u;
+constexpr unsigned kNoOwner = 0xFFFFu;
+
+template <int TS, int H> struct KDims {
+    using C = KCfg<TS, H>;
+    static constexpr int TW = TS + 2 * H + 2;                  // cell table side: tile + halo + one guard ring (never occupied)
+    static constexpr int NC = TW * TW, NC4 = (NC + 3) / 4 * 4;
+    static constexpr int RW = (TW + 31) / 32 + 1;              // occupancy words per table row (+1: funnel shifts read one past)
+    static constexpr int BM = (TW * RW + 3) / 4 * 4;           // one occupancy map, padded to 16 bytes
+    static constexpr int NW = C::T / 32;
+    static_assert(TS >= 2 * H && C::KMAX < H && C::NMAX <= (int)kIdxMask && C::T % 32 == 0 && C::CAP <= 0xFFF, "configuration");
+    static_assert(TW <= 255, "cell codes pack row and column into 8 bits each");
+};
+
+template <int TS, int H> struct __align__(16) KSmem {
+    using C = KCfg<TS, H>;
+    using D = KDims<TS, H>;
+    struct Tables {
+        alignas(16) unsigned head[D::NC4];             // per cell: list heads, low half = even position buffer, high half = odd
+        alignas(16) unsigned bitmap[C::KMAX][D::BM];   // per sub-step: one occupancy bit per cell
+    };
+    double2 pos[2][C::NMAX];                 // positions, double buffered by sub-step (TMA destination: the buffer the previous tile left free)
+    double2 vel[C::NMAX];                    // velocities (only the owner lane of a particle touches them during the sub-steps)
+    double2 wres[D::NW][32];                 // per warp: contribution of listed pair e to its first particle
+    union alignas(16) {
+        Tables t;
+        double2 vland[C::NMAX];              // landing zone of the NEXT tile's velocities while this tile is stored (TMA destination)
+    } u;
+    unsigned wij[D::NW][32];                 // per warp: listed pairs, i | j << 16
+    unsigned short next[2][C::NMAX];         // list links, double buffered like the heads
+    unsigned short ccode[C::NMAX];           // table row << 8 | table column of a particle's current cell
+    unsigned short pcode[C::NMAX];           // pass 1 -> pass 2: pair count | list base << 2;  store phase: class << 12 | rank
+    int id[C::CAP];                          // ids of the tile's own stripe (halo particles that end up inside fetch theirs at store time)
+    unsigned short horig[C::T];          // halo particle -> its shared slot before the ring sort (id look-up at store time)
+    unsigned long long mbar;                 // TMA completion
+    int rsrc[2][kRanges], rlen[2][kRanges], rdst[2][kRanges];   // slot ranges of this tile / the next: global slot, length, first shared slot
+    int ncount[2];                           // particles of this tile's / the next tile's region
+    int nproc[8];                            // per sub-step: particles that are still processed (own + rings that still matter)
+    int ringcnt[8];
+    int segcnt[12], segoff[12];
+    int flags, hw_region, hw_stripe, hw_pairs;
+};
+
+static_assert(2 * (sizeof(KSmem<64, 4>) + 1024) <= 233472 && 2 * (sizeof(KSmem<64, 3>) + 1024) <= 233472,
+              "two CTAs of the 64-cell kernel must fit one SM's shared memory");
+
+// the ten ranges: neighbour (dr, dc) and the classes [cb, ce) of ITS stripe that lie within H cells of this tile
+__constant__ signed char kRangeTab[kRanges][4] = {
+    {0, 0, 0, 9},     // own stripe
+    {-1, 0, 4, 7},    // N neighbour: its bottom band  BR B BL
+    {1, 0, 0, 3},     // S neighbour: its top band     TL T TR
+    {0, -1, 2, 5},    // W neighbour: its right band   TR R BR
+    {0, 1, 6, 8},     // E neighbour: its left band    BL L ...
+    {0, 1, 0, 1},     //                               ... TL (the ring wraps)
+    {-1, -1, 4, 5},   // NW: BR corner
+    {-1, 1, 6, 7},    // NE: BL corner
+    {1, -1, 2, 3},    // SW: TR corner
+    {1, 1, 0, 1},     // SE: TL corner
+};
+
+struct KParams {
+    const double2 *pos_in, *vel_in;
+    const int *id_in, *hdr_in;
+    double2 *pos_out, *vel_out, *acc_out;
+    int *id_out, *hdr_out;
+    double2* acc_tmp;     // per CTA scratch (NMAX entries): accelerations of the last sub-step until the slots are known
+    int ntx, nty;         // tiles per side (global)
+    int tr_base;          // global tile row of local row 0
+    int lrow0, row_stride, ntiles;   // tile t of the launch lies in local row lrow0 + (t / ntx) * row_stride
+    int bincnt;
+    double size;
+    int nsub;             // steps fused in this launch (0: only re-partition the stripes)
+    double vlim;          // |v| component bound that keeps the halo argument valid for nsub steps: d / dt
+    int* err;
+    int seq;              // launch number (reported with the first error)
+    int ringsort;         // order the halo by ring and stop processing rings that no longer matter
+    // slabs with peer-memory exchange: the first / last owned tile row also stores its facing band and headers into the
+    // neighbour GPU's ghost row (pointers to slot 0 / header 0 of that ROW, parity written)
+    double2 *peer_pos[2], *peer_vel[2];
+    int *peer_id[2], *peer_hdr[2];
+    int last_lrow;
+};
+
+// ---- PTX helpers: mbarrier + 1-D bulk copy (TMA) --------------------------------------------------
+__device__ __forceinline__ unsigned k_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void k_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(k_smem_u32(bar)), "r"(parity), "r"(200000u)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void k_tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(k_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(k_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void k_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Rare path: exact walk of the 3x3 neighbourhood with canonical-order summation (particles with three or more
+// in-range neighbours, or whose pairs did not fit the warp's list).
+template <int TS, int H>
+static __device__ __noinline__ double2 kslow_force(const KSmem<TS, H>& S, int b, unsigned vb, int i, int cell) {
+    constexpr int TW = KDims<TS, H>::TW;
+    const double2* xy = S.pos[b];
+    const unsigned short* next = S.next[b];
+    const double2 pi = xy[i];
+    auto visit = [&](auto&& f) {
+#pragma unroll 1
+        for (int k = 0; k < 9; ++k) {
+            const unsigned w = S.u.t.head[cell + (k / 3 - 1) * TW + (k % 3 - 1)];
+            unsigned h = b ? w >> 16 : w & 0xFFFFu;
+            while (h >= vb) {
+                const unsigned j = h & kIdxMask;
+                const double2 pj = xy[j];
+                f(pj.x, pj.y, k);
+                h = next[j];
+            }
+        }
+    };
+    auto rank_of = [&](double, double, int k) { return visit_rank(k / 3 - 1, k % 3 - 1); };
+    double ax, ay;
+    int nb;
+    accumulate_force(pi.x, pi.y, visit, rank_of, ax, ay, nb);
+    return make_double2(ax, ay);
+}
+
+// ------------------------------------------------------------------------------------------
+// the K-step kernel
+// ------------------------------------------------------------------------------------------
+// ---- per-particle helpers --------------------------------------------------------------------------------------------
+// A particle's table cell: its exact cell, clamped to the box (reference semantics for x == size) and to the table interior
+// (only particles whose computed state is already worthless can leave the loaded region).
+template <int TW>
+__device__ __forceinline__ void k_table_cell(double x, double y, int rbase, int cbase, bool at_wall, int bincnt, int& lr, int& lc) {
+    int gr = __double2int_rd(div_by_bin(x)), gc = __double2int_rd(div_by_bin(y));
+    if (at_wall) {
+        gr = min(max(gr, 0), bincnt - 1);
+        gc = min(max(gc, 0), bincnt - 1);
+    }
+    lr = min(max(gr - rbase, 1), TW - 2);
+    lc = min(max(gc - cbase, 1), TW - 2);
+}
+// insert particle p into the list of its cell (table parity tb, entries tagged with sub-step number ver)
+template <int TS, int H>
+__device__ __forceinline__ void k_bin_particle(KSmem<TS, H>& S, int p, int lr, int lc, int tb, unsigned ver, unsigned* bm) {
+    constexpr int TW = KDims<TS, H>::TW, RW = KDims<TS, H>::RW;
+    unsigned* w = &S.u.t.head[lr * TW + lc];
+    const unsigned ent = (ver << kIdxBits) | (unsigned)p;
+    unsigned old = *w;
+    for (;;) {   // exchange one half of the word, keep the other (it belongs to the table that is being searched)
+        const unsigned nw = tb ? ((old & 0xFFFFu) | (ent << 16)) : ((old & 0xFFFF0000u) | ent);
+        const unsigned prev = atomicCAS(w, old, nw);
+        if (prev == old) break;
+        old = prev;
+    }
+    S.next[tb][p] = (unsigned short)(tb ? old >> 16 : old & 0xFFFFu);   // an older sub-step's entry ends the list
+    S.ccode[p] = (unsigned short)((lr << 8) | lc);
+    atomicOr(&bm[lr * RW + (lc >> 5)], 1u << (lc & 31));
+}
+// final cell -> owner test, class, rank inside the class
+template <int TS, int H>
+__device__ __forceinline__ void k_classify(KSmem<TS, H>& S, int p, int lr, int lc) {
+    const int er = lr - (H + 1), ec = lc - (H + 1);
+    unsigned oc = kNoOwner;
+    const bool mine = (unsigned)er < (unsigned)TS && (unsigned)ec < (unsigned)TS;
+    const int rb = er < H ? 0 : (er >= TS - H ? 2 : 1), cb = ec < H ? 0 : (ec >= TS - H ? 2 : 1);
+    const unsigned cls = (unsigned)((0x456387210ull >> (4 * (rb * 3 + cb))) & 0xFull);   // ring order TL T TR R BR B BL L M
+    // most particles are interior (class M): one shared atomic per warp for them instead of one per lane on the same word
+    const unsigned act = __activemask();
+    const unsigned mm = __ballot_sync(act, mine && cls == 8u);
+    if (mine) {
+        int rank;
+        if (cls == 8u) {
+            const int leader = __ffs((int)mm) - 1, lane = (int)(threadIdx.x & 31u);
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&S.segcnt[8], __popc(mm));
+            rank = __shfl_sync(mm, base, leader) + __popc(mm & ((1u << lane) - 1u));
+        } else {
+            rank = atomicAdd(&S.segcnt[cls], 1);
+        }
+        oc = (cls << 12) | (unsigned)min(rank, 0xFFF);
+    }
+    S.pcode[p] = (unsigned short)oc;
+}
+
+// One time step of the region in shared memory (everything between two __syncthreads of the kernel).
+
+// Returns (speed bound exceeded) << 31 | most pairs this warp listed.
+template <int TS, int H, bool kStoreAcc>
+static __device__ __forceinline__ unsigned kstep_substep(int s, int b, bool last, int rbase, int cbase, bool at_wall, int bincnt, double size,
+                                                      int vlim_hi, double2* acc_tmp) {
+    using C = KCfg<TS, H>;
+    using D = KDims<TS, H>;
+    constexpr int TW = D::TW, RW = D::RW, NW = D::NW;
+    extern __shared__ __align__(128) unsigned char k_smem_raw[];
+    KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool too_fast = false;
+    {
+        const unsigned vb = (unsigned)(s + 1) << kIdxBits;   // entries of this sub-step are >= vb
+        const double2* posb = S.pos[b];
+        double2* posn = S.pos[b ^ 1];
+        const unsigned short* next = S.next[b];
+        const unsigned short* headh = reinterpret_cast<const unsigned short*>(S.u.t.head) + b;   // this parity's half of every head word
+        const unsigned* bm = S.u.t.bitmap[s];
+        const int np = S.nproc[s], nch = (np + 31) >> 5;
+        int wbase = 0;
+        // pass 1: candidate search, exact distance test
+#pragma unroll 1
+        for (int ch = warp; ch < nch; ch += NW) {
+            const int p = ch * 32 + lane;
+            int fc = 0;
+            unsigned cand = 0;   // the last two in-range neighbours, 16 bits each
+            if (p < np) {
+                const int cc = S.ccode[p];
+                const int lr = cc >> 8, lc = cc & 0xFF;
+                const int cell = lr * TW + lc;
+                const double2 me = posb[p];
+                // 9 occupancy bits of the 3x3 neighbourhood, bit 8*(dr+1) + (dc+1)
+                const unsigned* rb = bm + (lr - 1) * RW + ((lc - 1) >> 5);
+                const unsigned sh = (unsigned)(lc - 1) & 31u;
+                unsigned m = 0;
+#pragma unroll
+                for (int dr = 0; dr < 3; ++dr) m |= (__funnelshift_r(rb[dr * RW], rb[dr * RW + 1], sh) & 7u) << (8 * dr);
+                if (headh[2 * cell] == (unsigned short)(vb | (unsigned)p) && next[p] < vb) m &= ~(1u << 9);   // alone in my own cell
+                const unsigned short* hcorner = headh + 2 * (cell - TW - 1);
+#pragma unroll 1
+                while (m) {
+                    const int k = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    unsigned h = hcorner[(k >> 3) * (2 * TW) + 2 * (k & 7)];
+#pragma unroll 1
+                    do {   // the occupancy bit guarantees a non-empty list
+                        const unsigned j = h & kIdxMask;
+                        const double2 pj = posb[j];
+                        const unsigned hn = next[j];
+                        const double dx = __dsub_rn(pj.x, me.x), dy = __dsub_rn(pj.y, me.y);
+                        const double r2 = pair_r2(dx, dy);
+                        if (!(r2 > kCutoff2) && j != (unsigned)p) {
+                            cand = (cand << 16) | j;
+                            ++fc;
+                        }
+                        h = hn;
+                    } while (h >= vb);
+                }
+            }
+            // list the pairs of particles with one or two in-range neighbours: slots from two ballots, no atomics
+            const bool one = fc == 1 || fc == 2, two = fc == 2;
+            const unsigned m1 = __ballot_sync(0xffffffffu, one), m2 = __ballot_sync(0xffffffffu, two);
+            unsigned code = fc >= 3 ? 3u : 0u;
+            if (one) {
+                const int base = wbase + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
+                if (base + fc <= 32) {
+                    S.wij[warp][base] = (unsigned)p | (cand << 16);
+                    if (two) S.wij[warp][base + 1] = (unsigned)p | (cand & 0xFFFF0000u);
+                    code = (unsigned)fc | ((unsigned)base << 2);
+                } else {
+                    // no room: exact path.  A reserved entry below 32 must still be well formed for the evaluation:
+                    // a self pair (distance 0) contributes nothing.
+                    if (base < 32) S.wij[warp][base] = (unsigned)p | ((unsigned)p << 16);
+                    code = 3u;
+                }
+            }
+            wbase += __popc(m1) + __popc(m2);
+            if (p < np) S.pcode[p] = (unsigned short)code;
+        }
+        __syncwarp();
+        // dense evaluation of the warp's pairs: one lane per pair
+        if (lane < min(wbase, 32)) {
+            const unsigned ij = S.wij[warp][lane];
+            const double2 a = posb[ij & 0xFFFFu], c = posb[ij >> 16];
+            const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
+            const double r2 = pair_r2(dx, dy);
+            double cx = 0.0, cy = 0.0;
+            if (!(r2 > kCutoff2) && r2 != 0.0) pair_contrib(dx, dy, r2, cx, cy);
+            S.wres[warp][lane] = make_double2(cx, cy);
+        }
+        __syncwarp();
+        // pass 2: sum, move, speed check, next cell
+#pragma unroll 1
+        for (int ch = warp; ch < nch; ch += NW) {
+            const int p = ch * 32 + lane;
+            if (p < np) {
+                const unsigned code = S.pcode[p], fc = code & 3u;
+                const double2 me = posb[p];
+                double2 v = S.vel[p];
+                double x = me.x, y = me.y, ax = 0.0, ay = 0.0;
+                if (fc == 3u) {
+                    const int cc = S.ccode[p];
+                    const double2 a = kslow_force<TS, H>(S, b, vb, p, (cc >> 8) * TW + (cc & 0xFF));
+                    ax = a.x;
+                    ay = a.y;
+                } else if (fc != 0u) {
+                    const double2 c0_ = S.wres[warp][code >> 2];
+                    ax = __dadd_rn(ax, c0_.x);
+                    ay = __dadd_rn(ay, c0_.y);
+                    if (fc == 2u) {
+                        const double2 c1_ = S.wres[warp][(code >> 2) + 1];
+                        ax = __dadd_rn(ax, c1_.x);
+                        ay = __dadd_rn(ay, c1_.y);
+                    }
+                }
+                // integrate (reference serial.cpp:46-51); walls (serial.cpp:53-61) only where the loaded region touches one:
+                // elsewhere a particle that reaches a wall has left the trusted part of the region anyway
+                v.x = __dadd_rn(v.x, __dmul_rn(ax, kDt));
+                v.y = __dadd_rn(v.y, __dmul_rn(ay, kDt));
+                x = __dadd_rn(x, __dmul_rn(v.x, kDt));
+                y = __dadd_rn(y, __dmul_rn(v.y, kDt));
+                if (at_wall) reflect_particle(x, y, v.x, v.y, size);
+                too_fast |= max(__double2hiint(v.x) & 0x7FFFFFFF, __double2hiint(v.y) & 0x7FFFFFFF) >= vlim_hi;
+                posn[p] = make_double2(x, y);
+                S.vel[p] = v;
+                int lr, lc;
+                k_table_cell<TW>(x, y, rbase, cbase, at_wall, bincnt, lr, lc);
+                if (!last) {
+                    k_bin_particle<TS, H>(S, p, lr, lc, b ^ 1, (unsigned)(s + 2), S.u.t.bitmap[s + 1]);
+                } else {
+                    k_classify<TS, H>(S, p, lr, lc);
+                    if (kStoreAcc) acc_tmp[p] = make_double2(ax, ay);
+                }
+            }
+        }
+        return (too_fast ? 0x80000000u : 0u) | (unsigned)min(wbase, 0xFFFF);
+    }
+}
+
+
+template <int TS, int H, bool kStoreAcc, bool kPeer>
+__global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kernel(const KParams P) {
+    using C = KCfg<TS, H>;
+    using D = KDims<TS, H>;
+    constexpr int T = C::T, CAP = C::CAP, NMAX = C::NMAX, TW = D::TW, RW = D::RW, NW = D::NW;
+    constexpr int kIdRegs = (CAP + T - 1) / T;
+
+    extern __shared__ __align__(128) unsigned char k_smem_raw[];
+    KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
+
+    // an earlier launch hit a capacity / speed bound: leave the state untouched so that the host can replay it
+    if (*reinterpret_cast<volatile int*>(P.err + 8) != 0) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int nsub = P.nsub;
+    const int vlim_hi = __double2hiint(P.vlim);   // speeds are compared by the high words of their absolute values
+    const int G = gridDim.x;
+
+    if (tid == 0) {
+        k_mbar_init(&S.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.flags = 0;
+        S.hw_region = S.hw_stripe = S.hw_pairs = 0;
+    }
+    if (tid < 9) S.segcnt[tid] = 0;
+    if (tid < 8) S.ringcnt[tid] = 0;
+    bool too_fast = false;
+    int hw_pairs = 0;
+
+    // ---- loader (warp 0) ---------------------------------------------------------------------------------------------------
+    // Slot range `lane` (< kRanges) of the region of launch tile t: length and first global slot.  The headers of a tile are
+    // fetched one tile before its bulk copies are issued, the bulk copies one tile before the data is used.
+    // (the loader is the LAST warp: it has the fewest particle chunks; tiles are walked without divisions)
+    constexpr int kLoader = NW - 1;
+    const int walk_q = (G / P.ntx) * P.row_stride, walk_r = G % P.ntx;
+    struct Walk {
+        int t, lrow, tc;
+    };
+    auto advance = [&](Walk& w) {
+        w.t += G;
+        w.tc += walk_r;
+        w.lrow += walk_q;
+        if (w.tc >= P.ntx) {
+            w.tc -= P.ntx;
+            w.lrow += P.row_stride;
+        }
+    };
+    Walk cur{(int)blockIdx.x, P.lrow0 + ((int)blockIdx.x / P.ntx) * P.row_stride, (int)blockIdx.x % P.ntx};
+    Walk fw = cur;   // the tile whose headers are fetched next
+    const int rt_dr = lane < kRanges ? kRangeTab[lane][0] : 0, rt_dc = lane < kRanges ? kRangeTab[lane][1] : 0;
+    const int rt_cb = lane < kRanges ? kRangeTab[lane][2] : 0, rt_ce = lane < kRanges ? kRangeTab[lane][3] : 0;
+    auto fetch_range = [&](int& len, int& src) {
+        len = 0;
+        src = 0;
+        if (fw.t < P.ntiles && lane < kRanges && (lane == 0 || nsub > 0)) {
+            const int ntr = P.tr_base + fw.lrow + rt_dr, ntc = fw.tc + rt_dc;
+            if (ntr >= 0 && ntr < P.nty && ntc >= 0 && ntc < P.ntx) {
+                const int nlt = (fw.lrow + rt_dr) * P.ntx + ntc;
+                const int* h = P.hdr_in + (size_t)nlt * kHdrInts;
+                len = max(min(h[rt_ce], CAP) - min(h[rt_cb], CAP), 0);
+                src = nlt * CAP + min(h[rt_cb], CAP);
+            }
+        }
+        advance(fw);
+    };
+    // Publish the ranges of a tile in slot set q and issue its bulk copies: positions into position buffer pb, velocities into
+    // the landing zone (the cell table's storage, dead between the last search of a tile and the wipe of the next one).
+    auto issue_load = [&](int len, int src, int q, int pb) {
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += a;
+        }
+        int dst = inc - len;
+        const int total = __shfl_sync(0xffffffffu, inc, kRanges - 1);
+        if (total > NMAX) {   // region does not fit: truncate (memory safety) and report
+            dst = min(dst, NMAX);
+            len = min(len, NMAX - dst);
+        }
+        const int n = min(total, NMAX);
+        if (lane < kRanges) {
+            S.rsrc[q][lane] = src;
+            S.rlen[q][lane] = len;
+            S.rdst[q][lane] = dst;
+        }
+        if (lane == 0) {
+            S.ncount[q] = n;
+            if (total > NMAX) atomicOr(&S.flags, kErrSmemOverflow);
+            S.hw_region = max(S.hw_region, total);
+            k_mbar_arrive_expect_tx(&S.mbar, (unsigned)n * 32u);
+        }
+        __syncwarp();
+        if (len > 0) {
+            k_tma_load_1d(&S.pos[pb][dst], P.pos_in + src, (unsigned)len * 16u, &S.mbar);
+            k_tma_load_1d(&S.u.vland[dst], P.vel_in + src, (unsigned)len * 16u, &S.mbar);
+        }
+    };
+    int next_len = 0, next_src = 0;
+    __syncthreads();   // mbarrier initialised
+    if (warp == kLoader) {
+        fetch_range(next_len, next_src);
+        issue_load(next_len, next_src, 0, 0);
+        fetch_range(next_len, next_src);
+    }
+
+    int b0 = 0;   // position buffer that holds the tile's initial positions
+    for (int it = 0; cur.t < P.ntiles; ++it, advance(cur)) {
+        const int q = it & 1, t = cur.t;
+        const int lrow = cur.lrow, tc = cur.tc;
+        const int rbase = (P.tr_base + lrow) * TS - H - 1, cbase = tc * TS - H - 1;   // global cell of table row / column 0
+        const bool at_wall = rbase + 1 <= 0 || cbase + 1 <= 0 || rbase + TW - 2 >= P.bincnt - 1 || cbase + TW - 2 >= P.bincnt - 1;
+
+        // a particle's table cell: its exact cell, clamped to the box (reference semantics for x == size) and to the table
+        // interior (only particles whose computed state is already worthless can leave the loaded region)
+        auto table_cell = [&](double x, double y, int& lr, int& lc) { k_table_cell<TW>(x, y, rbase, cbase, at_wall, P.bincnt, lr, lc); };
+
+        // ---- arrival: velocities leave the landing zone, the halo is ordered by ring -----------------------------------
+        k_mbar_wait(&S.mbar, (unsigned)q);
+        const int n = S.ncount[q];
+        const int n_own = S.rlen[q][0], own_src = S.rsrc[q][0], n_halo = n - n_own;
+        // ids of the tile's own stripe (range 0, shared slots [0, n_own)): loaded now, parked in shared memory after the
+        // barrier below; the few halo particles that end up inside the tile fetch theirs when they are stored
+        int idreg[kIdRegs];
+#pragma unroll
+        for (int k = 0; k < kIdRegs; ++k) idreg[k] = tid + k * T < n_own ? P.id_in[own_src + tid + k * T] : 0;
+        for (int p = tid; p < n_own; p += T) S.vel[p] = S.u.vland[p];
+        // A halo particle at ring r (cells between it and the tile, 1..H) can influence the tile's final state only through
+        // sub-step H - 1 - r, and nothing reads it after sub-step H - r: sorted by ring, the particles that still matter are a
+        // prefix of the region, and the passes of sub-step s simply stop at n_proc[s].  (Skipped when the halo exceeds one
+        // particle per thread.)  Ring and class counters were zeroed at the end of the previous tile.
+        const bool ringsort = P.ringsort && nsub > 0 && n_halo <= T;
+        double2 hpos = make_double2(0.0, 0.0), hvel = make_double2(0.0, 0.0);
+        int hring = 0, hrank = 0;
+        if (ringsort) {
+            if (tid < n_halo) {
+                hpos = S.pos[b0][n_own + tid];
+                hvel = S.u.vland[n_own + tid];
+                int lr, lc;
+                table_cell(hpos.x, hpos.y, lr, lc);
+                const int er = lr - (H + 1), ec = lc - (H + 1);
+                const int dr = er < 0 ? -er : (er >= TS ? er - TS + 1 : 0), dc = ec < 0 ? -ec : (ec >= TS ? ec - TS + 1 : 0);
+                hring = min(max(max(dr, dc), 1), H);
+                hrank = atomicAdd(&S.ringcnt[hring], 1);
+            }
+        } else {
+            for (int p = n_own + tid; p < n; p += T) S.vel[p] = S.u.vland[p];
+        }
+        __syncthreads();   // the landing zone is free (it becomes the cell table again); ring counts complete
+        if (ringsort) {
+            if (tid < n_halo) {
+                int o = n_own + hrank;
+                for (int r = 1; r < hring; ++r) o += S.ringcnt[r];
+                S.pos[b0][o] = hpos;
+                S.vel[o] = hvel;
+                S.horig[o - n_own] = (unsigned short)(n_own + tid);
+            }
+            if (tid < C::KMAX) {   // sub-step tid processes rings <= H - 1 - tid
+                int c = n_own;
+                for (int r = 1; r <= H - 1 - tid; ++r) c += S.ringcnt[r];
+                S.nproc[tid] = c;
+            }
+        } else if (tid < C::KMAX) {
+            S.nproc[tid] = n;
+        }
+#pragma unroll
+        for (int k = 0; k < kIdRegs; ++k)
+            if (tid + k * T < n_own) S.id[tid + k * T] = idreg[k];
+        {   // wipe the cell table and the occupancy maps
+            uint4* hq = reinterpret_cast<uint4*>(S.u.t.head);
+            for (int c = tid; c < D::NC4 / 4; c += T) hq[c] = make_uint4(0u, 0u, 0u, 0u);
+            uint4* bq = reinterpret_cast<uint4*>(&S.u.t.bitmap[0][0]);
+            for (int c = tid; c < C::KMAX * D::BM / 4; c += T) bq[c] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+
+        if (nsub == 0) {
+            for (int p = tid; p < n; p += T) {
+                const double2 a = S.pos[b0][p];
+                int lr, lc;
+                table_cell(a.x, a.y, lr, lc);
+                k_classify<TS, H>(S, p, lr, lc);
+            }
+        } else {
+            for (int p = tid; p < n; p += T) {
+                const double2 a = S.pos[b0][p];
+                int lr, lc;
+                table_cell(a.x, a.y, lr, lc);
+                k_bin_particle<TS, H>(S, p, lr, lc, b0, 1u, S.u.t.bitmap[0]);
+            }
+        }
+        k_fence_proxy_async();   // (only matters for nsub == 0: the barrier below is then the last one before the next bulk copies)
+        __syncthreads();
+
+        // ---- the fused time steps ----------------------------------------------------------------------------------
+        for (int s = 0; s < nsub; ++s) {
+            const unsigned r = kstep_substep<TS, H, kStoreAcc>(s, (b0 + s) & 1, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size,
+                                                               vlim_hi, P.acc_tmp + (size_t)blockIdx.x * NMAX);
+            too_fast |= (r >> 31) != 0u;
+            hw_pairs = max(hw_pairs, (int)(r & 0xFFFFu));
+            if (s + 1 == nsub) k_fence_proxy_async();   // my accesses to the cell table and the free position buffer precede the next tile's bulk copies
+            __syncthreads();
+        }
+
+
+        // ---- store phase: the loader warp issues the next tile's bulk copies while the other warps store this tile ----------
+        const int bf = (b0 + nsub) & 1;   // buffer with the final positions; the other one receives the next tile
+        if (warp == kLoader) {
+            if (cur.t + G < P.ntiles) {
+                issue_load(next_len, next_src, q ^ 1, bf ^ 1);
+                fetch_range(next_len, next_src);
+            }
+        } else {
+            constexpr int TS_ = T - 32;   // storing threads (named barrier 1)
+            // class offsets -> header, particles -> the other parity's stripe
+            if (warp == 0) {
+                int v = lane < 9 ? S.segcnt[lane] : 0, inc = v;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const int a = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += a;
+                }
+                if (lane < 10) S.segoff[lane] = inc - v;   // exclusive prefix; [9] = population
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TS_) : "memory");
+            const int lrow_ = cur.lrow, tc_ = cur.tc, lt = lrow_ * P.ntx + tc_;
+            const size_t gbase = (size_t)lt * CAP;
+            double2* ppos = nullptr;
+            double2* pvel = nullptr;
+            int *pid = nullptr, *phdr = nullptr;
+            unsigned peer_classes = 0;   // bit c: class c also goes to the neighbour slab
+            if (kPeer) {
+                // first owned row -> lower neighbour (needs my top band TL T TR); last owned row -> upper neighbour (BR B BL).
+                // A one-row slab would have to serve both: such slabs use the NCCL flavour (kstep host code).
+                const int side = lrow_ == 1 ? 0 : (lrow_ == P.last_lrow ? 1 : -1);
+                if (side >= 0 && P.peer_pos[side]) {
+                    ppos = P.peer_pos[side] + (size_t)tc_ * CAP;
+                    pvel = P.peer_vel[side] + (size_t)tc_ * CAP;
+                    pid = P.peer_id[side] + (size_t)tc_ * CAP;
+                    phdr = P.peer_hdr[side] + (size_t)tc_ * kHdrInts;
+                    peer_classes = side == 0 ? 0x007u : 0x070u;
+                }
+            }
+            if (tid < 10) {
+                const int o = min(S.segoff[tid], CAP);
+                P.hdr_out[(size_t)lt * kHdrInts + tid] = o;
+                if (kPeer && phdr) phdr[tid] = o;
+                if (tid == 9) {
+                    if (S.segoff[9] > CAP) atomicOr(&S.flags, kErrTileOverflow);
+                    S.hw_stripe = max(S.hw_stripe, S.segoff[9]);
+                }
+            }
+            const double2* posf = S.pos[bf];
+            const int nfin = nsub > 0 ? S.nproc[nsub - 1] : S.ncount[q];   // particles beyond were never candidates for the tile
+            const int n_own_ = S.rlen[q][0];
+            const bool sorted = P.ringsort && nsub > 0 && S.ncount[q] - n_own_ <= T;
+#pragma unroll 1
+            for (int p = tid; p < nfin; p += TS_) {
+                const unsigned oc = S.pcode[p];
+                if (oc == kNoOwner) continue;
+                const unsigned cls = oc >> 12;
+                const int d = S.segoff[cls] + (int)(oc & 0xFFFu);
+                if (d >= CAP) continue;
+                const double2 pq = posf[p], v = S.vel[p];
+                int id;
+                if (p < n_own_) {
+                    id = S.id[p];
+                } else {   // a halo particle that moved into the tile: find its source slot
+                    const int po = sorted ? (int)S.horig[p - n_own_] : p;   // its slot before the ring sort
+                    id = 0;
+                    for (int g = 1; g < kRanges; ++g) {
+                        const int o = po - S.rdst[q][g];
+                        if ((unsigned)o < (unsigned)S.rlen[q][g]) id = P.id_in[S.rsrc[q][g] + o];
+                    }
+                }
+                P.pos_out[gbase + d] = pq;
+                P.vel_out[gbase + d] = v;
+                P.id_out[gbase + d] = id;
+                if (kStoreAcc) P.acc_out[gbase + d] = nsub > 0 ? P.acc_tmp[(size_t)blockIdx.x * NMAX + p] : make_double2(0.0, 0.0);
+                if (kPeer && ((peer_classes >> cls) & 1u)) {
+                    ppos[d] = pq;
+                    pvel[d] = v;
+                    pid[d] = id;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TS_) : "memory");   // class counters have been read by everybody
+            if (tid < 9) S.segcnt[tid] = 0;
+            if (tid < 8) S.ringcnt[tid] = 0;
+        }
+        b0 = bf ^ 1;
+        __syncthreads();   // the tile is completely stored: velocities, codes and the final position buffer may be overwritten
+    }
+    // ---- report ------------------------------------------------------------------------------------------------------
+    if (__any_sync(0xffffffffu, too_fast) && lane == 0) atomicOr(&S.flags, kErrSpeedBound);
+    for (int o = 16; o > 0; o >>= 1) hw_pairs = max(hw_pairs, __shfl_xor_sync(0xffffffffu, hw_pairs, o));
+    if (lane == 0) atomicMax(&S.hw_pairs, hw_pairs);
+    __syncthreads();
+    if (tid == 0) {
+        if (S.flags) {
+            atomicOr(P.err, S.flags);
+            atomicCAS(P.err + 8, 0, P.seq + 1);   // later launches become no-ops: the input of launch `seq` stays intact
+        }
+        atomicMax(P.err + 3, S.hw_stripe);
+        atomicMax(P.err + 4, S.hw_region);
+        atomicMax(P.err + 7, S.hw_pairs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// initial tiling and observation
+// ------------------------------------------------------------------------------------------
+// one thread per input record: owned tile rows only; arrival order inside a stripe is arbitrary (forces are summed in a
+// canonical order); the stripes are partitioned into classes by a 0-step launch afterwards
+__global__ void __launch_bounds__(256) kstep_fill_kernel(const particle_t* __restrict__ p, int n, int id0, int bincnt, int ts,
+                                                         int cap, int ntx, int tr_begin, int tr_end, int tr_base,
+                                                         double2* __restrict__ pos, double2* __restrict__ vel,
+                                                         int* __restrict__ sid, int* __restrict__ tcount, int* __restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2* q = reinterpret_cast<const double2*>(p + i);
+    const double2 a = q[0], b = q[1];
+    const int tr = axis_cell(a.x, bincnt) / ts, tc = axis_cell(a.y, bincnt) / ts;
+    if (tr < tr_begin || tr >= tr_end) return;
+    const int lt = (tr - tr_base) * ntx + tc;
+    const int slot = atomicAdd(tcount + lt, 1);
+    if (slot >= cap) {
+        atomicOr(err, kErrTileOverflow);
+        return;
+    }
+    const size_t d = (size_t)lt * cap + slot;
+    pos[d] = a;
+    vel[d] = b;
+    sid[d] = id0 + i;
+}
+
+// headers of the freshly filled (unpartitioned) stripes: everything counts as class M
+__global__ void __launch_bounds__(256) kstep_hdr_init_kernel(const int* __restrict__ tcount, int ntiles, int cap, int* __restrict__ hdr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntiles * kHdrInts) return;
+    const int c = i % kHdrInts;
+    hdr[i] = c == 9 ? min(tcount[i / kHdrInts], cap) : 0;
+}
+
+// gather the owned particles into a compact SoA (observation calls); one CTA per owned tile
+__global__ void __launch_bounds__(128) kstep_gather_kernel(const double2* __restrict__ pos, const double2* __restrict__ vel,
+                                                           const int* __restrict__ sid, const int* __restrict__ hdr,
+                                                           const double2* __restrict__ acc, int cap, int ntx, bool have_acc,
+                                                           double* __restrict__ gx, double* __restrict__ gy,
+                                                           double* __restrict__ gvx, double* __restrict__ gvy,
+                                                           double* __restrict__ gax, double* __restrict__ gay,
+                                                           int* __restrict__ gid, int* __restrict__ cursor) {
+    __shared__ int s_base;
+    const int lt = (1 + blockIdx.x / ntx) * ntx + blockIdx.x % ntx;   // owned rows start at local row 1
+    const int n = min(hdr[(size_t)lt * kHdrInts + 9], cap);
+    if (threadIdx.x == 0) s_base = n ? atomicAdd(cursor, n) : 0;
+    __syncthreads();
+    const int base = s_base;
+    const size_t gbase = (size_t)lt * cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 p = pos[gbase + i], v = vel[gbase + i];
+        const double2 a = have_acc ? acc[gbase + i] : make_double2(0.0, 0.0);
+        gx[base + i] = p.x;
+        gy[base + i] = p.y;
+        gvx[base + i] = v.x;
+        gvy[base + i] = v.y;
+        gax[base + i] = a.x;
+        gay[base + i] = a.y;
+        gid[base + i] = sid[gbase + i];
+    }
+}
+
+// Write-back in ORIGINAL particle order straight from the stripes (the drivers' view of `parts`, reference
+// part1/main.cpp:135-136 / part3/main.cu:134-136): out[id] = {x y vx vy ax ay}, or only xy[id] = {x y}.
+__global__ void __launch_bounds__(128) kstep_writeback_kernel(const double2* __restrict__ pos, const double2* __restrict__ vel,
+                                                              const int* __restrict__ sid, const int* __restrict__ hdr,
+                                                              const double2* __restrict__ acc, int cap, int ntx, bool have_acc,
+                                                              particle_t* __restrict__ out, double2* __restrict__ out_xy) {
+    const int lt = (1 + blockIdx.x / ntx) * ntx + blockIdx.x % ntx;
+    const int n = min(hdr[(size_t)lt * kHdrInts + 9], cap);
+    const size_t gbase = (size_t)lt * cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int id = sid[gbase + i];
+        const double2 p = pos[gbase + i];
+        if (out_xy) {
+            out_xy[id] = p;
+        } else {
+            double2* q = reinterpret_cast<double2*>(out + id);
+            q[0] = p;
+            q[1] = vel[gbase + i];
+            q[2] = have_acc ? acc[gbase + i] : make_double2(0.0, 0.0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct KLaunchRec {   // what the host needs to replay a launch
+    int seq, nsub, parity_in;
+    bool store;
+    long long steps_before;
+};
+
+struct KstepEngine {
+    DeviceArena mem;
+    int ts = 0, h = 0, kmax = 0, cap = 0, nmax = 0, threads = 0, ctas_per_sm = 1;
+    size_t smem = 0;
+    int sms = 148;
+    int ntx = 0;
+    int tr_begin = 0, tr_end = 0, lrows = 0, lrows_alloc = 0;
+    int ksteps = 4;                 // steps fused per launch (PSIM_KSTEPS, <= kmax)
+    int ringsort = 1;               // PSIM_RINGSORT=0 disables the halo ring culling
+    // stripes + headers, double buffered by launch parity; one allocation per parity (its CUDA IPC handle is shared with
+    // the neighbour slabs): [headers | pos | vel | id]
+    char* buf[2] = {nullptr, nullptr};
+    size_t buf_bytes = 0, off_pos = 0, off_vel = 0, off_id = 0;
+    double2 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr}, *acc = nullptr, *acc_tmp = nullptr;
+    int *sid[2] = {nullptr, nullptr}, *hdr[2] = {nullptr, nullptr};
+    int* tcount = nullptr;
+    int parity = 0;
+    bool acc_valid = false;
+    bool ghost_fresh = false;
+    int grid_cap = 0;
+    int seq = 0;                    // launches issued so far
+    std::vector<KLaunchRec> log;    // launches since the last successful synchronisation
+    int recoveries = 0;
+    // gather scratch
+    DeviceArena gmem;
+    SoAView g{};
+    int* g_cursor = nullptr;
+    int g_capacity = 0;
+};
+
+void tiled_slab_rows(int ntx, int rank, int nranks, int* begin, int* end);   // psim_tiled.cu
+int tiled_tile_rows(int bincnt, int ts);
+
+static KParams kmake_params(psim_sim* sim, KstepEngine* e, int parity_in) {
+    KParams P{};
+    const int po = parity_in ^ 1;
+    P.pos_in = e->pos[parity_in]; P.vel_in = e->vel[parity_in]; P.id_in = e->sid[parity_in]; P.hdr_in = e->hdr[parity_in];
+    P.pos_out = e->pos[po]; P.vel_out = e->vel[po]; P.id_out = e->sid[po]; P.hdr_out = e->hdr[po];
+    P.acc_out = e->acc;
+    P.acc_tmp = e->acc_tmp;
+    P.ntx = e->ntx;
+    P.nty = e->ntx;
+    P.tr_base = e->tr_begin - 1;
+    P.lrow0 = 1;
+    P.row_stride = 1;
+    P.ntiles = e->lrows * e->ntx;
+    P.bincnt = sim->bincnt;
+    P.size = sim->size;
+    P.err = sim->d_err;
+    P.last_lrow = e->lrows;
+    P.ringsort = e->ringsort;
+    for (int side = 0; side < 2; ++side) {
+        P.peer_pos[side] = P.peer_vel[side] = nullptr;
+        P.peer_id[side] = P.peer_hdr[side] = nullptr;
+    }
+    if (sim->p2p) {
+        // the neighbour's buffer has the same [headers | pos | vel | id] layout; only its row count differs
+        for (int side = 0; side < 2; ++side) {
+            const int nb = side == 0 ? sim->rank - 1 : sim->rank + 1;
+            if (nb < 0 || nb >= sim->nranks || !sim->peer_exports[side][po]) continue;
+            int b, en;
+            tiled_slab_rows(e->ntx, nb, sim->nranks, &b, &en);
+            const size_t nb_rows_alloc = (size_t)(en - b) + 2;
+            const size_t grow = side == 0 ? (size_t)(en - b) + 1 : 0;   // its upper ghost row / its lower ghost row
+            char* base = sim->peer_exports[side][po];
+            const size_t nb_tiles = nb_rows_alloc * e->ntx, nb_slots = nb_tiles * e->cap;
+            auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+            const size_t o_pos = up(nb_tiles * kHdrInts * sizeof(int)), o_vel = o_pos + up(nb_slots * sizeof(double2)),
+                         o_id = o_vel + up(nb_slots * sizeof(double2));
+            P.peer_hdr[side] = reinterpret_cast<int*>(base) + grow * e->ntx * kHdrInts;
+            P.peer_pos[side] = reinterpret_cast<double2*>(base + o_pos) + grow * e->ntx * e->cap;
+            P.peer_vel[side] = reinterpret_cast<double2*>(base + o_vel) + grow * e->ntx * e->cap;
+            P.peer_id[side] = reinterpret_cast<int*>(base + o_id) + grow * e->ntx * e->cap;
+        }
+    }
+    return P;
+}
+
+template <int TS, int H>
+static int klaunch(psim_sim* sim, KstepEngine* e, KParams& P, bool store_acc, cudaStream_t s) {
+    const int grid = std::min(P.ntiles, e->grid_cap);
+    const bool peer = P.peer_pos[0] || P.peer_pos[1];
+    constexpr int kThreads = KCfg<TS, H>::T;
+    constexpr size_t kSmem = sizeof(KSmem<TS, H>);
+    if (store_acc) {
+        if (peer) kstep_kernel<TS, H, true, true><<<grid, kThreads, kSmem, s>>>(P);
+        else kstep_kernel<TS, H, true, false><<<grid, kThreads, kSmem, s>>>(P);
+    } else {
+        if (peer) kstep_kernel<TS, H, false, true><<<grid, kThreads, kSmem, s>>>(P);
+        else kstep_kernel<TS, H, false, false><<<grid, kThreads, kSmem, s>>>(P);
+    }
+    ++sim->launches;
+    return PSIM_OK;
+}
+
+// one launch over local tile rows lrow0, lrow0 + stride, ... (nrows of them)
+static int klaunch_rows(psim_sim* sim, KstepEngine* e, int parity_in, int nsub, bool store_acc, int seq, int lrow0, int nrows,
+                        int row_stride, bool allow_peer, cudaStream_t s) {
+    if (nrows <= 0) return PSIM_OK;
+    KParams P = kmake_params(sim, e, parity_in);
+    if (!allow_peer)
+        for (int side = 0; side < 2; ++side) P.peer_pos[side] = nullptr;
+    P.lrow0 = lrow0;
+    P.row_stride = row_stride;
+    P.ntiles = nrows * e->ntx;
+    P.nsub = nsub;
+    P.seq = seq;
+    // displacement bound per step that H halo cells allow for nsub fused steps, with a 2 % margin for the rounding of the
+    // region arithmetic: d = (H - nsub) / nsub cells  ->  |v| <= d * 0.01 / dt
+    P.vlim = nsub > 0 ? 0.98 * ((double)(e->h - nsub) / nsub) * PSIM_BIN_SIZE / PSIM_DT : 1e300;
+    switch (e->ts * 8 + e->h) {
+        case 16 * 8 + 3: return klaunch<16, 3>(sim, e, P, store_acc, s);
+        case 16 * 8 + 4: return klaunch<16, 4>(sim, e, P, store_acc, s);
+        case 32 * 8 + 3: return klaunch<32, 3>(sim, e, P, store_acc, s);
+        case 32 * 8 + 4: return klaunch<32, 4>(sim, e, P, store_acc, s);
+        case 64 * 8 + 3: return klaunch<64, 3>(sim, e, P, store_acc, s);
+        case 64 * 8 + 4: return klaunch<64, 4>(sim, e, P, store_acc, s);
+    }
+    return fail(PSIM_ERR_INVALID, "kstep tile size %d / halo %d not instantiated", e->ts, e->h);
+}
+
+template <int TS, int H>
+static int kconfigure(KstepEngine* e) {
+    e->h = H;
+    e->kmax = KCfg<TS, H>::KMAX;
+    e->cap = KCfg<TS, H>::CAP;
+    e->nmax = KCfg<TS, H>::NMAX;
+    e->threads = KCfg<TS, H>::T;
+    e->smem = sizeof(KSmem<TS, H>);
+    auto prepare = [&](auto kernel) -> int {
+        PSIM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+        PSIM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        return PSIM_OK;
+    };
+    PSIM_TRY(prepare(kstep_kernel<TS, H, true, true>));
+    PSIM_TRY(prepare(kstep_kernel<TS, H, true, false>));
+    PSIM_TRY(prepare(kstep_kernel<TS, H, false, true>));
+    PSIM_TRY(prepare(kstep_kernel<TS, H, false, false>));
+    int per_sm = 0;
+    PSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kstep_kernel<TS, H, false, false>, KCfg<TS, H>::T, e->smem));
+    e->ctas_per_sm = std::max(1, per_sm);
+    if (const char* cap = std::getenv("PSIM_CTAS_PER_SM")) {   // tuning / profiling knob
+        const int c = std::atoi(cap);
+        if (c >= 1) e->ctas_per_sm = std::min(e->ctas_per_sm, c);
+    }
+    return PSIM_OK;
+}
+
+int kstep_default_tile(int bincnt) {
+    // 64-cell tiles amortise the halo best (region / tile = 1.34); smaller boxes take smaller tiles so that there are
+    // enough tiles to spread over the SMs
+    const long long n64 = (bincnt + 63) / 64, n32 = (bincnt + 31) / 32;
+    if (n64 * n64 >= 592) return 64;
+    if (n32 * n32 >= 296) return 32;
+    return bincnt >= 64 ? 32 : 16;
+}
+
+int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts, int n, bool parts_on_device, bool* unsuitable) {
+    *unsuitable = false;
+    cudaStream_t s = sim->stream;
+    int ts = cfg->tile_cells;
+    if (ts == 0) ts = kstep_default_tile(sim->bincnt);
+    if (ts != 16 && ts != 32 && ts != 64) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32 or 64 (got %d)", ts);
+    auto* e = new KstepEngine();
+    sim->kstep = e;
+    e->ts = ts;
+    PSIM_CUDA(cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, sim->device));
+    int halo = 4;   // 4 halo cells / up to 3 fused steps; PSIM_HALO=3 selects 3 cells / up to 2 steps
+    if (const char* hv = std::getenv("PSIM_HALO")) halo = std::atoi(hv);
+    if (halo != 3 && halo != 4) return fail(PSIM_ERR_INVALID, "PSIM_HALO must be 3 or 4 (got %d)", halo);
+    if (ts == 16) PSIM_TRY(halo == 3 ? (kconfigure<16, 3>(e)) : (kconfigure<16, 4>(e)));
+    if (ts == 32) PSIM_TRY(halo == 3 ? (kconfigure<32, 3>(e)) : (kconfigure<32, 4>(e)));
+    if (ts == 64) PSIM_TRY(halo == 3 ? (kconfigure<64, 3>(e)) : (kconfigure<64, 4>(e)));
+    e->grid_cap = e->sms * e->ctas_per_sm;
+    e->ksteps = e->kmax;
+    if (const char* r = std::getenv("PSIM_RINGSORT")) e->ringsort = std::atoi(r) != 0;
+    if (const char* k = std::getenv("PSIM_KSTEPS")) e->ksteps = std::min(std::max(std::atoi(k), 1), e->kmax);
+    e->ntx = tiled_tile_rows(sim->bincnt, ts);
+    if (sim->nranks > e->ntx) return fail(PSIM_ERR_INVALID, "more slabs (%d) than tile rows (%d)", sim->nranks, e->ntx);
+    tiled_slab_rows(e->ntx, sim->rank, sim->nranks, &e->tr_begin, &e->tr_end);
+    e->lrows = e->tr_end - e->tr_begin;
+    e->lrows_alloc = e->lrows + 2;
+    sim->row_begin = e->tr_begin * ts;
+    sim->row_end = std::min(e->tr_end * ts, sim->bincnt);
+
+    const size_t tiles = (size_t)e->lrows_alloc * e->ntx, slots = tiles * e->cap;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    e->off_pos = up(tiles * kHdrInts * sizeof(int));
+    e->off_vel = e->off_pos + up(slots * sizeof(double2));
+    e->off_id = e->off_vel + up(slots * sizeof(double2));
+    e->buf_bytes = e->off_id + up(slots * sizeof(int));
+    for (int b = 0; b < 2; ++b) {
+        PSIM_TRY(e->mem.alloc(&e->buf[b], e->buf_bytes));
+        e->hdr[b] = reinterpret_cast<int*>(e->buf[b]);
+        e->pos[b] = reinterpret_cast<double2*>(e->buf[b] + e->off_pos);
+        e->vel[b] = reinterpret_cast<double2*>(e->buf[b] + e->off_vel);
+        e->sid[b] = reinterpret_cast<int*>(e->buf[b] + e->off_id);
+        PSIM_CUDA(cudaMemsetAsync(e->hdr[b], 0, tiles * kHdrInts * sizeof(int), s));
+    }
+    PSIM_TRY(e->mem.alloc(&e->acc, slots));
+    PSIM_TRY(e->mem.alloc(&e->acc_tmp, (size_t)e->grid_cap * e->nmax));
+    PSIM_TRY(e->mem.alloc(&e->tcount, tiles));
+    PSIM_CUDA(cudaMemsetAsync(e->tcount, 0, sizeof(int) * tiles, s));
+    // fill: device input is read in place; host input is streamed through a bounded staging buffer
+    {
+        DeviceArena stage;
+        particle_t* d_stage = nullptr;
+        const int chunk = parts_on_device ? n : std::min(n, 4 << 20);
+        if (!parts_on_device && n > 0) PSIM_TRY(stage.alloc(&d_stage, (size_t)chunk));
+        for (int off = 0; off < n; off += chunk) {
+            const int m = std::min(chunk, n - off);
+            const particle_t* src = parts + off;
+            if (!parts_on_device) {
+                PSIM_CUDA(cudaMemcpyAsync(d_stage, parts + off, sizeof(particle_t) * (size_t)m, cudaMemcpyHostToDevice, s));
+                src = d_stage;
+            }
+            kstep_fill_kernel<<<(m + 255) / 256, 256, 0, s>>>(src, m, off, sim->bincnt, ts, e->cap, e->ntx, e->tr_begin, e->tr_end,
+                                                              e->tr_begin - 1, e->pos[0], e->vel[0], e->sid[0], e->tcount,
+                                                              sim->d_err);
+            ++sim->launches;
+        }
+        PSIM_CUDA(cudaGetLastError());
+        if (!parts_on_device) PSIM_CUDA(cudaStreamSynchronize(s));   // the staging buffer is freed below
+        stage.release();
+    }
+    // suitability: the densest tile must leave headroom for fluctuations, else the caller falls back
+    {
+        std::vector<int> h(tiles);
+        PSIM_CUDA(cudaMemcpyAsync(h.data(), e->tcount, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, s));
+        PSIM_CUDA(cudaStreamSynchronize(s));
+        int worst = 0;
+        for (int v : h) worst = std::max(worst, v);
+        // the region (tile + halo) of the densest neighbourhood must fit shared memory too: bound it by the area ratio
+        const double region_ratio = (double)(ts + 2 * e->h) * (ts + 2 * e->h) / ((double)ts * ts);
+        if (worst + worst / 8 + 16 > e->cap || worst * region_ratio * 1.05 + 16 > e->nmax) {
+            *unsuitable = true;
+            PSIM_CUDA(cudaMemsetAsync(sim->d_err, 0, sizeof(int), s));
+            return fail(PSIM_ERR_UNSUPPORTED, "kstep engine: densest %dx%d-cell tile holds %d particles (stripe capacity %d, region capacity %d)",
+                        ts, ts, worst, e->cap, e->nmax);
+        }
+    }
+    kstep_hdr_init_kernel<<<((int)tiles * kHdrInts + 255) / 256, 256, 0, s>>>(e->tcount, (int)tiles, e->cap, e->hdr[0]);
+    ++sim->launches;
+    // partition the stripes into classes: a 0-step launch from parity 0 into parity 1
+    PSIM_TRY(klaunch_rows(sim, e, 0, 0, true, e->seq++, 1, e->lrows, 1, false, s));
+    PSIM_CUDA(cudaGetLastError());
+    e->parity = 1;
+    e->acc_valid = true;   // zeros
+    return PSIM_OK;
+}
+
+int kstep_exchange(psim_sim* sim, int parity, cudaStream_t s);   // psim_comm.cpp
+
+// issue one launch (all owned rows) of nsub steps; slabs split it into a boundary and an interior launch
+static int kstep_issue(psim_sim* sim, KstepEngine* e, int nsub, bool store) {
+    cudaStream_t s = sim->stream;
+    const int seq = e->seq++;
+    if (e->log.size() >= (1u << 16)) e->log.erase(e->log.begin(), e->log.begin() + (1u << 15));   // (a caller that never synchronises)
+    e->log.push_back({seq, nsub, e->parity, store, sim->steps_done});
+    if (sim->nranks == 1) {
+        PSIM_TRY(klaunch_rows(sim, e, e->parity, nsub, store, seq, 1, e->lrows, 1, false, s));
+    } else if (sim->p2p) {
+        // Peer-memory flavour (same choreography as the tiled engine, once per LAUNCH instead of once per step): the first and
+        // last owned tile rows go first on the high-priority stream and store their facing bands straight into the neighbours'
+        // ghost rows; a flag then tells the neighbours that my boundary rows of this launch are done.  My boundary rows may
+        // start once both neighbours have flagged the previous launch.  Boundary and interior launches of one batch touch
+        // disjoint tiles and run concurrently; each depends on BOTH launches of the previous batch.
+        if (!e->ghost_fresh) {
+            PSIM_TRY(kstep_exchange(sim, e->parity, s));
+            e->ghost_fresh = true;
+        }
+        cudaStream_t sb = sim->comm_stream;
+        const unsigned k = sim->p2p_steps & 1u, kp = k ^ 1u;
+        if (sim->p2p_steps == 0) {
+            PSIM_CUDA(cudaEventRecord(sim->ev_i[kp], s));
+            PSIM_CUDA(cudaEventRecord(sim->ev_b[kp], s));
+        }
+        PSIM_CUDA(cudaStreamWaitEvent(sb, sim->ev_i[kp], 0));
+        PSIM_TRY(comm_p2p_wait(sim, sb));
+        if (e->lrows <= 2) PSIM_TRY(klaunch_rows(sim, e, e->parity, nsub, store, seq, 1, e->lrows, 1, true, sb));
+        else PSIM_TRY(klaunch_rows(sim, e, e->parity, nsub, store, seq, 1, 2, e->lrows - 1, true, sb));
+        PSIM_CUDA(cudaEventRecord(sim->ev_b[k], sb));
+        PSIM_TRY(comm_p2p_signal(sim, sb));
+        PSIM_CUDA(cudaStreamWaitEvent(s, sim->ev_b[kp], 0));
+        if (e->lrows > 2) PSIM_TRY(klaunch_rows(sim, e, e->parity, nsub, store, seq, 2, e->lrows - 2, 1, false, s));
+        PSIM_CUDA(cudaEventRecord(sim->ev_i[k], s));
+        PSIM_CUDA(cudaStreamWaitEvent(s, sim->ev_b[k], 0));   // the handle's stream always covers the whole batch
+    } else {
+        // NCCL flavour: boundary rows first, their rows travel on the exchange stream while the interior rows are computed
+        if (!e->ghost_fresh) {
+            PSIM_TRY(kstep_exchange(sim, e->parity, s));
+            e->ghost_fresh = true;
+        }
+        if (e->lrows <= 2) PSIM_TRY(klaunch_rows(sim, e, e->parity, nsub, store, seq, 1, e->lrows, 1, false, s));
+        else PSIM_TRY(klaunch_rows(sim, e, e->parity, nsub, store, seq, 1, 2, e->lrows - 1, false, s));
+        PSIM_CUDA(cudaEventRecord(sim->ev_boundary, s));
+        PSIM_CUDA(cudaStreamWaitEvent(sim->comm_stream, sim->ev_boundary, 0));
+        PSIM_TRY(kstep_exchange(sim, e->parity ^ 1, sim->comm_stream));
+        PSIM_CUDA(cudaEventRecord(sim->ev_exchanged, sim->comm_stream));
+        if (e->lrows > 2) PSIM_TRY(klaunch_rows(sim, e, e->parity, nsub, store, seq, 2, e->lrows - 2, 1, false, s));
+        PSIM_CUDA(cudaStreamWaitEvent(s, sim->ev_exchanged, 0));
+    }
+    e->parity ^= 1;
+    e->acc_valid = store;
+    sim->steps_done += nsub;
+    return PSIM_OK;
+}
+
+int kstep_step(psim_sim* sim, int nsteps, int flags) {
+    KstepEngine* e = sim->kstep;
+    if (sim->nranks > 1 && !sim->comm) return fail(PSIM_ERR_STATE, "slab %d/%d is not connected: call psim_comm_connect first", sim->rank, sim->nranks);
+    const int kmax = (flags & PSIM_STEP_ACCEL_ALL) ? 1 : e->ksteps;
+    int done = 0;
+    while (done < nsteps) {
+        const int k = std::min(kmax, nsteps - done);
+        const bool store = (flags & PSIM_STEP_ACCEL_ALL) || (!(flags & PSIM_STEP_ACCEL_NONE) && done + k == nsteps);
+        PSIM_TRY(kstep_issue(sim, e, k, store));
+        done += k;
+    }
+    PSIM_CUDA(cudaGetLastError());
+    return PSIM_OK;
+}
+
+// Called with the stream synchronised and the error words in sim->h_err.  No failed launch: forget the log.  A launch that
+// exceeded the speed bound: rewind to its (untouched) input and replay it one step per launch -- the halo argument then
+// allows a displacement of H - 1 cells per step -- followed by the launches that were skipped.  Returns PSIM_OK if the
+// caller should synchronise and check again (`*replayed` set), or PSIM_ERR_CAPACITY; in that case *pending_steps >= 0 says
+// that the state was rewound to the failed launch's input and how many enqueued steps are still owed.
+int kstep_after_sync(psim_sim* sim, bool* replayed, int* pending_steps, bool* pending_store) {
+    KstepEngine* e = sim->kstep;
+    *replayed = false;
+    *pending_steps = -1;
+    *pending_store = false;
+    const int failed = sim->h_err[8];
+    if (failed == 0) {
+        e->log.clear();
+        return PSIM_OK;
+    }
+    const int flags = sim->h_err[0];
+    const int seq = failed - 1;
+    size_t at = 0;
+    while (at < e->log.size() && e->log[at].seq != seq) ++at;
+    const bool known = at < e->log.size();
+    if ((flags & ~kErrSpeedBound) || !known || sim->nranks > 1 || e->log[at].nsub <= 1) {
+        // capacity overflows, slabs (the neighbours have moved on) and a speed beyond even the one-step bound are not recoverable
+        if (known) {   // the input of the failed launch is still intact: rewind to it; the caller may finish the batch on another engine
+            e->parity = e->log[at].parity_in;
+            sim->steps_done = e->log[at].steps_before;
+            e->acc_valid = false;
+            *pending_steps = 0;
+            for (size_t r = at; r < e->log.size(); ++r) {
+                *pending_steps += e->log[r].nsub;
+                *pending_store = e->log[r].store;
+            }
+        }
+        e->log.clear();
+        return PSIM_ERR_CAPACITY;
+    }
+    std::vector<KLaunchRec> redo(e->log.begin() + at, e->log.end());
+    e->log.clear();
+    e->parity = redo[0].parity_in;
+    sim->steps_done = redo[0].steps_before;
+    PSIM_CUDA(cudaMemsetAsync(sim->d_err, 0, 9 * sizeof(int), sim->stream));
+    ++e->recoveries;
+    for (size_t r = 0; r < redo.size(); ++r) {
+        if (r == 0) {
+            for (int k = 0; k < redo[0].nsub; ++k) PSIM_TRY(kstep_issue(sim, e, 1, redo[0].store && k == redo[0].nsub - 1));
+        } else {
+            PSIM_TRY(kstep_issue(sim, e, redo[r].nsub, redo[r].store));
+        }
+    }
+    PSIM_CUDA(cudaGetLastError());
+    *replayed = true;
+    return PSIM_OK;
+}
+
+int kstep_view(psim_sim* sim, SoAView* out) {
+    KstepEngine* e = sim->kstep;
+    cudaStream_t s = sim->stream;
+    // scratch sized by what this slab can own (every owned stripe full), not by the global particle count
+    const int capacity = (int)std::min<long long>((long long)sim->n_total, (long long)e->lrows * e->ntx * e->cap);
+    if (!e->g_cursor || e->g_capacity < capacity) {
+        e->gmem.release();
+        const size_t c = (size_t)capacity + 2;
+        PSIM_TRY(e->gmem.reserve(c * (6 * sizeof(double) + sizeof(int)) + 8 * 256 + 256));
+        PSIM_TRY(e->gmem.alloc(&e->g.x, c));
+        PSIM_TRY(e->gmem.alloc(&e->g.y, c));
+        PSIM_TRY(e->gmem.alloc(&e->g.vx, c));
+        PSIM_TRY(e->gmem.alloc(&e->g.vy, c));
+        PSIM_TRY(e->gmem.alloc(&e->g.ax, c));
+        PSIM_TRY(e->gmem.alloc(&e->g.ay, c));
+        PSIM_TRY(e->gmem.alloc(&e->g.id, c));
+        PSIM_TRY(e->gmem.alloc(&e->g_cursor, 1));
+        e->g_capacity = capacity;
+    }
+    PSIM_CUDA(cudaMemsetAsync(e->g_cursor, 0, sizeof(int), s));
+    const int p = e->parity;
+    if (e->lrows * e->ntx > 0)
+        kstep_gather_kernel<<<e->lrows * e->ntx, 128, 0, s>>>(e->pos[p], e->vel[p], e->sid[p], e->hdr[p], e->acc, e->cap, e->ntx,
+                                                              e->acc_valid, e->g.x, e->g.y, e->g.vx, e->g.vy, e->g.ax, e->g.ay,
+                                                              e->g.id, e->g_cursor);
+    ++sim->launches;
+    PSIM_CUDA(cudaGetLastError());
+    int n = 0;
+    PSIM_CUDA(cudaMemcpyAsync(&n, e->g_cursor, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PSIM_CUDA(cudaStreamSynchronize(s));
+    *out = e->g;
+    out->n = n;
+    return PSIM_OK;
+}
+
+// original-order write-back into a DEVICE buffer of n_total records (exactly one of d_out / d_xy); enqueued on the handle's stream
+int kstep_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy) {
+    KstepEngine* e = sim->kstep;
+    const int p = e->parity;
+    if (e->lrows * e->ntx > 0)
+        kstep_writeback_kernel<<<e->lrows * e->ntx, 128, 0, sim->stream>>>(e->pos[p], e->vel[p], e->sid[p], e->hdr[p], e->acc, e->cap,
+                                                                           e->ntx, e->acc_valid, d_out, d_xy);
+    ++sim->launches;
+    PSIM_CUDA(cudaGetLastError());
+    return PSIM_OK;
+}
+
+void kstep_destroy(psim_sim* sim) {
+    KstepEngine* e = sim->kstep;
+    if (!e) return;
+    e->gmem.release();
+    e->mem.release();
+    delete e;
+    sim->kstep = nullptr;
+}
+
+long long kstep_bytes(psim_sim* sim) { return sim->kstep ? (long long)(sim->kstep->mem.bytes + sim->kstep->gmem.bytes) : 0; }
+
+void kstep_info(psim_sim* sim, psim_info_t* out) {
+    KstepEngine* e = sim->kstep;
+    out->tile_cells = e->ts;
+    out->tiles_per_side = e->ntx;
+    out->tile_capacity = e->cap;
+    out->halo_cells = e->h;
+    out->steps_per_launch = e->ksteps;
+    out->region_capacity = e->nmax;
+    out->recoveries = e->recoveries;
+}
+
+// accessors for psim_comm.cpp: the buffers shared with the neighbour slabs and the four byte ranges that make up one tile row
+void kstep_shared_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, int* ntx) {
+    KstepEngine* e = sim->kstep;
+    *parity0 = e->buf[0];
+    *parity1 = e->buf[1];
+    *bytes = e->buf_bytes;
+    *ntx = e->ntx;
+}
+
+void kstep_row_ranges(psim_sim* sim, int parity, int lrow, char* ptr[4], size_t bytes[4]) {
+    KstepEngine* e = sim->kstep;
+    const size_t t0 = (size_t)lrow * e->ntx, s0 = t0 * e->cap;
+    ptr[0] = reinterpret_cast<char*>(e->hdr[parity] + t0 * kHdrInts);
+    bytes[0] = (size_t)e->ntx * kHdrInts * sizeof(int);
+    ptr[1] = reinterpret_cast<char*>(e->pos[parity] + s0);
+    bytes[1] = (size_t)e->ntx * e->cap * sizeof(double2);
+    ptr[2] = reinterpret_cast<char*>(e->vel[parity] + s0);
+    bytes[2] = bytes[1];
+    ptr[3] = reinterpret_cast<char*>(e->sid[parity] + s0);
+    bytes[3] = (size_t)e->ntx * e->cap * sizeof(int);
+}
+
+int kstep_owned_rows(psim_sim* sim) { return sim->kstep->lrows; }
+
+}  // namespace psim

@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 BUILD = os.path.join(CSRC, "build")
 
-ENGINE_AUTO, ENGINE_CELLSORT, ENGINE_TILED = 0, 1, 2
+ENGINE_AUTO, ENGINE_CELLSORT, ENGINE_TILED, ENGINE_KSTEP = 0, 1, 2, 3
 STEP_DEFAULT, STEP_ACCEL_ALL, STEP_ACCEL_NONE = 0, 1, 2
 
 # every symbol include/psim.h declares (tests check that the library exports each of them)
@@ -57,7 +57,9 @@ class Info(C.Structure):
                 ("nranks", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("steps_done", C.c_longlong),
                 ("kernel_launches", C.c_longlong), ("device_bytes", C.c_longlong), ("hw_leavers", C.c_int),
                 ("hw_halo_list", C.c_int), ("hw_tile_population", C.c_int), ("hw_apron", C.c_int),
-                ("outbox_capacity", C.c_int), ("halo_list_capacity", C.c_int), ("reserved_hw_pairs", C.c_int)]
+                ("outbox_capacity", C.c_int), ("halo_list_capacity", C.c_int), ("reserved_hw_pairs", C.c_int),
+                ("halo_cells", C.c_int), ("steps_per_launch", C.c_int), ("region_capacity", C.c_int),
+                ("recoveries", C.c_int), ("engine_switches", C.c_int)]
 
 
 def lib_path() -> str:

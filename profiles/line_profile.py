@@ -13,7 +13,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(root, "parallel-particle-simulation_b200", "csrc", "build", "libpsim.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if "tiled" in f][0]
+cubin = [f for f in os.listdir(tmp) if (sys.argv[5] if len(sys.argv) > 5 else "tiled") in f][0]
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 line_of, cur, infn = {}, None, False
 for l in sass.splitlines():

@@ -19,12 +19,14 @@ from psim_testlib import GOLDEN_DIR, REF_DIR, RefKernel, box_size, have_ref, loa
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["cellsort", "tiled16", "tiled32", "tiled64"]
+ENGINES = ["cellsort", "tiled16", "tiled32", "tiled64", "kstep16", "kstep32", "kstep64"]
 
 
 def make_sim(pkg, parts, size, engine):
     if engine == "cellsort":
         return pkg.Simulation(parts, len(parts), size, engine=pkg.ENGINE_CELLSORT)
+    if engine.startswith("kstep"):
+        return pkg.Simulation(parts, len(parts), size, engine=pkg.ENGINE_KSTEP, tile_cells=int(engine[5:]))
     return pkg.Simulation(parts, len(parts), size, engine=pkg.ENGINE_TILED, tile_cells=int(engine[5:]))
 
 
@@ -43,7 +45,7 @@ def test_cells_match_reference_bins_bit_exact(pkg, engine, fixture, step):
     sim.close()
 
 
-@pytest.mark.parametrize("engine", ["cellsort", "tiled32"])
+@pytest.mark.parametrize("engine", ["cellsort", "tiled32", "kstep32"])
 def test_cell_lists_match_oracle(pkg, oracle, engine):
     n = 20000
     size = box_size(n)
@@ -153,7 +155,7 @@ def test_against_live_reference_kernel_100k(pkg):
 
 
 # ---------------------------------------------------------------- edge cases
-@pytest.mark.parametrize("engine", ["cellsort", "tiled16"])
+@pytest.mark.parametrize("engine", ["cellsort", "tiled16", "kstep16", "kstep64"])
 def test_edge_cases(pkg, oracle, engine):
     size = box_size(1000)
     cases = {
@@ -180,7 +182,7 @@ def test_edge_cases(pkg, oracle, engine):
         sim.close()
 
 
-@pytest.mark.parametrize("engine", ["cellsort", "tiled16", "tiled32"])
+@pytest.mark.parametrize("engine", ["cellsort", "tiled16", "tiled32", "kstep16", "kstep64"])
 def test_pair_list_overflow_takes_the_exact_path(pkg, oracle, engine):
     """More candidate pairs inside one tile than the tiled engine's shared-memory pair list holds (32 entries for
     16-cell tiles, 64 for 32-cell tiles): a serpentine chain, every particle with two neighbours at 0.8 cutoff.
@@ -200,8 +202,10 @@ def test_pair_list_overflow_takes_the_exact_path(pkg, oracle, engine):
         got = sim.step(1).sync().read_particles()
         assert np.array_equal(got, want)
     assert np.abs(want[:, 4:]).max() > 0
-    if engine != "cellsort":
+    if engine.startswith("tiled"):
         assert sim.info()["reserved_hw_pairs"] > (32 if engine == "tiled16" else 64)
+    if engine.startswith("kstep"):
+        assert sim.info()["reserved_hw_pairs"] > 32   # more pairs than one warp's list holds
     sim.close()
 
 
