@@ -69,15 +69,6 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def recorded_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -153,13 +144,25 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
         "steps": k, "warmup": w, "ms_per_step": 1e3 * r["steps_s"] / k, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n} particles, density 0.0005, cutoff 0.01, seed {args.seed}", "particles": n,
-                   "requested_steps": args.steps, "init_simulation_s": r["init_s"]},
+        "config": {"workload": workload_string(n, args.seed), "baseline_config": baseline_config(n, args.gpus, args.scaling),
+                   "particles": n, "requested_steps": args.steps, "init_simulation_s": r["init_s"]},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": r["threads"], "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_string(n, seed):
+    """identical in both arms (the driver compares config.workload)"""
+    return f"{n} particles, density 0.0005, cutoff 0.01, seed {seed}, reference generator (part1/main.cpp:31-59)"
+
+
+def baseline_config(n, world, scaling):
+    if scaling == "weak" and world > 1:
+        return "configs[4] weak scaling, 20 M particles per GPU"
+    return {20_000_000: "configs[3] 20 M particles", 1_000_000: "configs[2] 1 M particles (state fits L2: not an HBM case)",
+            100_000: "configs[1] 100 k particles (launch-latency bound)"}.get(n, "-")
 
 
 def main():
@@ -193,6 +196,18 @@ def main():
     host = torch.empty((n, 6), dtype=torch.float64, pin_memory=True)
     pkg.init_particles(n, args.seed, size, out=host.numpy())
 
+    def allreduce(value, op, dtype=torch.float64):
+        t = torch.tensor([value], dtype=dtype, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return t.item()
+
+    def fingerprint(sim):
+        """order-independent 64-bit state hash summed over the slabs (mod 2^64) + number of owned particles over all slabs"""
+        h, owned = sim.state_hash()
+        hs = allreduce(h - (1 << 64) if h >= (1 << 63) else h, dist.ReduceOp.SUM if world > 1 else None, torch.int64)
+        return f"{int(hs) & ((1 << 64) - 1):016x}", int(allreduce(owned, dist.ReduceOp.SUM if world > 1 else None, torch.int64))
+
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         sim = pkg.Simulation(host, n, size, engine=engine, device=local, stream=stream.cuda_stream,
@@ -225,17 +240,32 @@ def main():
         ms = ev0.elapsed_time(ev1)
         sim.sync()
         clocks = sampler.stop() if rank == 0 else None
-        launches = sim.info()["kernel_launches"] - launches0
         info = sim.info()
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        launches = info["kernel_launches"] - launches0
+        ms = float(allreduce(ms, dist.ReduceOp.MAX if world > 1 else None))
         value = n * args.steps / (ms * 1e-3)
 
-        # sanity on the state that was just timed: every particle still inside the box
+        # ---- checks on the state that was just timed (assertions, not decoration) ---------------------
+        state_hash, owned_total = fingerprint(sim)
+        xy = torch.full((n, 2), float("nan"), dtype=torch.float64, device="cuda")
+        sim.read_positions(xy)   # a slab writes only the particles it owns
+        mine = ~torch.isnan(xy[:, 0])
+        inside = bool(((xy[mine] >= 0.0) & (xy[mine] <= size)).all().item())
+        inside = bool(allreduce(1.0 if inside else 0.0, dist.ReduceOp.MIN if world > 1 else None) == 1.0)
+        del xy, mine
         st = sim.stats()
+        pairs = int(allreduce(st["pairs"], dist.ReduceOp.SUM if world > 1 else None, torch.int64))
+        ke = float(allreduce(st["kinetic_energy"], dist.ReduceOp.SUM if world > 1 else None))
+        dmin = float(allreduce(st["dmin"], dist.ReduceOp.MIN if world > 1 else None))
+        vmax = float(allreduce(st["vmax"], dist.ReduceOp.MAX if world > 1 else None))
+        recoveries = int(allreduce(info["recoveries"], dist.ReduceOp.SUM if world > 1 else None, torch.int64))
+        switches = int(allreduce(info["engine_switches"], dist.ReduceOp.SUM if world > 1 else None, torch.int64))
+        steps_done = info["steps_done"]
         sim.close()
+        assert owned_total == n, f"the slabs own {owned_total} particles, expected {n}"
+        assert inside, "a particle left the box"
+        assert steps_done == args.prewarm + args.warmup + args.steps, steps_done
+        assert 0.5 < dmin <= 1.0 and vmax < 20.0, (dmin, vmax)
 
         # ---- end to end through the C ABI with host buffers -----------------------------------------
         e2e = None
@@ -245,20 +275,27 @@ def main():
             t0 = time.perf_counter()
             sim2 = pkg.Simulation(host, n, size, engine=engine, device=local, stream=stream.cuda_stream,
                                   tile_cells=args.tile, rank=rank, nranks=world)
+            t1 = time.perf_counter()
             if world > 1:
                 sim2.comm_connect(uid[0])   # same id: the process-level communicator is reused (like MPI_COMM_WORLD)
+            t2 = time.perf_counter()
             sim2.step(args.steps, pkg.STEP_DEFAULT)
-            sim2.read_particles(host)
+            sim2.sync()
+            t3 = time.perf_counter()
+            sim2.read_particles(host)   # every rank: the particles it owns, into its pinned host array
             barrier()
-            dt = time.perf_counter() - t0
-            te = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dt = float(te.item())
+            t4 = time.perf_counter()
+            dt = float(allreduce(t4 - t0, dist.ReduceOp.MAX if world > 1 else None))
+            e2e_hash, e2e_owned = fingerprint(sim2)
             sim2.close()
+            assert e2e_owned == n
+            per_gpu = n / world
             e2e = {"value": n * args.steps / dt, "unit": "particle-steps/s", "seconds": dt,
-                   "h2d_bytes_per_step": 48.0 * n / args.steps, "d2h_bytes_per_step": 48.0 * n / args.steps,
-                   "what": "psim_create(pinned host AoS) + psim_step(K) + psim_read_particles(host AoS), wall clock"}
+                   "h2d_bytes_per_step": 48.0 * n / args.steps, "d2h_bytes_per_step": 48.0 * per_gpu / args.steps,
+                   "phases_s_rank0": {"create_h2d": t1 - t0, "connect": t2 - t1, "steps": t3 - t2, "read_back_d2h": t4 - t3},
+                   "state_hash_after_init_plus_steps": e2e_hash,
+                   "what": "per rank: psim_create(pinned host AoS of ALL particles: H2D + slab filter) + psim_step(K) + "
+                           "psim_read_particles(owned records -> pinned host AoS), wall clock, max over ranks"}
 
     if rank != 0:
         if world > 1:
@@ -267,26 +304,49 @@ def main():
 
     peak, peak_src = measured_peak()
     per_gpu_particles = n / world
-    launches_per_step = max(1, round(launches / args.steps))
+    kstep = info["engine"] == pkg.ENGINE_KSTEP
+    k = max(1, info["steps_per_launch"]) if kstep else 1
+    step_launches = max(1, round(launches * k / args.steps))  # kernels per batch of k steps on this rank
     achieved = ALGO_BYTES * per_gpu_particles / (ms * 1e-3 / args.steps) / 1e9
-    traffic = recorded_traffic()
+    engine_name = {pkg.ENGINE_TILED: "tiled", pkg.ENGINE_KSTEP: "kstep"}.get(info["engine"], "cellsort")
+    if kstep:
+        ts, h = info["tile_cells"], info["halo_cells"]
+        region = (ts + 2 * h) ** 2 / float(ts * ts)
+        # per launch of k steps: read x y vx vy of the region (tile + halo), ids of the tile; write x y vx vy id of the tile
+        moved = (32.0 * region + 4.0 + 36.0) / k
+        kernel = f"kstep_kernel<{ts},{h}> ({k} steps fused per launch)"
+    else:
+        moved = 72.0 if engine_name == "tiled" else None
+        kernel = "tile_step_kernel" if engine_name == "tiled" else "hist+scan+scatter+force_move (4 kernels)"
     line = {
         "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n} particles, density 0.0005, cutoff 0.01, seed {args.seed} "
-                               f"(BASELINE configs[{4 if args.scaling == 'weak' and world > 1 else 3 if n == 20_000_000 else 2 if n == 1_000_000 else 1 if n == 100_000 else '-'}])",
-                   "particles": n, "engine": {pkg.ENGINE_TILED: "tiled", pkg.ENGINE_KSTEP: "kstep"}.get(info["engine"], "cellsort"), "steps_per_launch": info["steps_per_launch"], "halo_cells": info["halo_cells"], "recoveries": info["recoveries"],
-                   "tile_cells": info["tile_cells"], "slabs": world, "l2": "state (>= 640 MB per GPU at 20 M) larger than L2; no flush needed",
-                   "accel_store": "last step of the batch", "device_bytes": info["device_bytes"]},
+        "config": {"workload": workload_string(n, args.seed), "baseline_config": baseline_config(n, world, args.scaling),
+                   "particles": n, "engine": engine_name, "tile_cells": info["tile_cells"], "halo_cells": info["halo_cells"],
+                   "steps_per_launch": info["steps_per_launch"], "slabs": world,
+                   "untimed_steps_before": args.prewarm + args.warmup,
+                   "l2": "state (>= 640 MB per GPU at 20 M) larger than the 126 MB L2; no flush needed" if per_gpu_particles >= 4e6
+                         else "state fits L2: the HBM roofline fraction is not meaningful at this size",
+                   "accel_store": "ax, ay materialised for the last step of the batch (the reference drivers never read them)",
+                   "device_bytes": info["device_bytes"]},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                     "algorithmic_bytes_per_launch": ALGO_BYTES * per_gpu_particles / launches_per_step,
-                     "kernel": "tile_step_kernel" if info["engine"] == pkg.ENGINE_TILED else "hist+scan+scatter+force_move (4 kernels)",
-                     "launches_per_step": launches_per_step, "peak_source": peak_src},
+                     "traffic": None,
+                     "algorithmic_bytes_per_particle_step": ALGO_BYTES,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES * per_gpu_particles * k / step_launches,
+                     "bytes_moved_per_particle_step_model": moved,
+                     "frac_of_peak_on_bytes_moved": (moved * per_gpu_particles / (ms * 1e-3 / args.steps) / 1e9 / peak) if moved else None,
+                     "kernel": kernel, "launches_per_batch": step_launches, "steps_per_launch": k, "peak_source": peak_src,
+                     "note": "achieved = 80 algorithmic bytes x particle-steps/s (SURVEY 8d). The kstep kernel keeps a tile K steps in "
+                             "shared memory, so it MOVES fewer bytes than that (model above; ncu dram bytes under profiles/) and is bound "
+                             "by shared-memory / issue throughput, not HBM. traffic is null here: it is only quoted from an ncu capture."},
         "clocks": clocks,
-        "check": {"pairs": st["pairs"], "dmin": st["dmin"], "davg": st["davg"], "kinetic_energy": st["kinetic_energy"]},
+        "check": {"state_hash": state_hash, "owned_particles": owned_total, "all_inside_box": inside, "steps_done": steps_done,
+                  "pairs_within_slabs": pairs, "dmin": dmin, "vmax": vmax, "kinetic_energy": ke, "speed_bound_replays": recoveries,
+                  "engine_switches": switches,
+                  "note": "state_hash = sum over all slabs of a 64-bit mix of (id, x, y, vx, vy): identical for 1/2/4/8 GPUs iff the "
+                          "states are bit-identical; asserted: every particle owned exactly once and inside the box"},
     }
     if e2e:
         line["e2e"] = e2e

@@ -21,6 +21,8 @@
  *                                               part3/main.cu:134-136 (device array + cudaMemcpy D2H)
  *   psim_read_cells        the bin structure    part1/serial.cpp:14-16,41-43,84-86;
  *                                               part3/gpu.cu:92-112 (Bins / Bin_Sizes)
+ *   psim_gather            gather_for_save      part2/common.h:32, part2/mpi.cpp:371-402 (MPI flavour; the 5-argument
+ *                                               entry points themselves are exported by csrc/psim_mpi_shim.cpp)
  *   psim_stats             (no reference code; validation statistics of SURVEY.md section 8c-5)
  *   psim_init_particles    init_particles       part1/main.cpp:31-59
  *   psim_save_frame        save                 part1/main.cpp:15-28 (same bytes; std::to_chars formatter,
@@ -111,6 +113,7 @@ typedef struct psim_info_t {
     int steps_per_launch;  /* K: time steps fused per kernel launch (PSIM_KSTEPS, default 4)     */
     int region_capacity;   /* particles of one tile + halo region the kernel can hold            */
     int recoveries;        /* batches replayed one step per launch after a speed-bound violation  */
+    int input_on_device;   /* psim_create was handed a device pointer (part3/main.cu flavour)    */
     int engine_switches;   /* kstep -> cellsort hand-overs (stripe / region overflow, or a particle faster than
                               the one-step halo bound): the handle keeps running on the cellsort engine */
 } psim_info_t;
@@ -125,6 +128,8 @@ const char* psim_last_error(void);
  * its timer starts (its cudaMalloc at part3/main.cu:120-122 precedes the clock at :125); a host-pointer driver would
  * otherwise pay it inside init_simulation.  Optional: psim_create does it implicitly. */
 int psim_device_init(int device);
+/* number of visible CUDA devices (the multi-process shim spreads its ranks over them) */
+int psim_device_count(int* count);
 /* Page-lock (or release) a caller-owned host array so that the read-backs into it run at full PCIe speed.  Optional;
  * the drop-in shim does it for the driver's `parts` array, which it is handed on every call anyway. */
 int psim_host_register(void* host_ptr, size_t bytes);
@@ -162,6 +167,11 @@ int psim_read_cells(psim_sim* sim, int* cell_of_particle, int* cell_counts);
  * members has num_parts entries, members of a cell in ascending original index.  HOST pointers. */
 int psim_read_cell_lists(psim_sim* sim, int* cell_start, int* members);
 int psim_stats(psim_sim* sim, psim_stats_t* out);
+/* Fingerprint of the particles this handle owns: the sum (mod 2^64) over particles of a 64-bit mix of the original
+ * index and the bits of x, y, vx, vy -- independent of storage order, tile size, engine and slab count, so the sums of
+ * all slabs of one run add up to the same number as the single-GPU run (bench.py check.state_hash).  `owned` (may be
+ * NULL) receives the number of particles hashed. */
+int psim_state_hash(psim_sim* sim, unsigned long long* hash, long long* owned);
 int psim_info(psim_sim* sim, psim_info_t* out);
 
 /* ---- driver helpers (host side) ---- */
@@ -177,11 +187,16 @@ int psim_save_frame(void* file, const double* xy, int num_parts, double size, in
 /* ---- multi-GPU slab exchange (one process per GPU) ---- */
 /* The slab decomposition the engine uses (precedent: reference part2/mpi.cpp:258-270, rows of cells along x split
  * contiguously over the ranks): cell rows [*row_begin, *row_end) of a box with `bin_count` cells per side belong to
- * `rank` of `nranks` when tiles are `tile_cells` cells wide (0 = the engine's default for that box).  Host only. */
+ * `rank` of `nranks` when tiles are `tile_cells` cells wide (0 = the default engine's choice for that box).  Host only. */
 int psim_slab_rows(int bin_count, int tile_cells, int rank, int nranks, int* row_begin, int* row_end);
 /* 128-byte NCCL unique id: rank 0 creates it, the launcher broadcasts it, every rank connects. */
 int psim_comm_unique_id(unsigned char id128[128]);
 int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]);
+/* Collective over the slabs (every rank calls it): rank `root` receives ALL particles, in original order, in `dst`
+ * (host or device array of num_parts_total records; ignored on the other ranks).  The reference's gather_for_save
+ * (part2/common.h:32, part2/mpi.cpp:371-402: every rank sends its particles to rank 0, which places them by id); here the
+ * records travel GPU to GPU over NCCL and are placed by a kernel. */
+int psim_gather(psim_sim* sim, particle_t* dst, int root);
 
 #ifdef __cplusplus
 }

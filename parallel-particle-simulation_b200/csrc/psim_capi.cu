@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "psim_device.cuh"
 #include "psim_internal.h"
@@ -62,6 +63,15 @@ __global__ void __launch_bounds__(kObsThreads) soa_pack_kernel(SoAView v, bool h
     q[2] = have_acc ? make_double2(v.ax[i], v.ay[i]) : make_double2(0.0, 0.0);
 }
 
+// gathered records (any order) + their original indices -> AoS in original order
+__global__ void __launch_bounds__(kObsThreads) place_records_kernel(const particle_t* __restrict__ rec, const int* __restrict__ ids, int n,
+                                                                    particle_t* __restrict__ out) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;   // three lanes per 48-byte record
+    const int i = u / 3, piece = u - 3 * i;
+    if (i >= n) return;
+    reinterpret_cast<double2*>(out + ids[i])[piece] = reinterpret_cast<const double2*>(rec + i)[piece];
+}
+
 __global__ void __launch_bounds__(kObsThreads) cell_of_particle_kernel(SoAView v, int bincnt, int* __restrict__ cell_of) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
@@ -97,6 +107,26 @@ __global__ void __launch_bounds__(kObsThreads) sort_xy_kernel(SoAView v, int bin
     const int d = cell_start[c] + slot[i];
     sx[d] = v.x[i];
     sy[d] = v.y[i];
+}
+
+// order-independent fingerprint of the owned particles: sum over particles of a 64-bit mix of (id, x, y, vx, vy) bits
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(kObsThreads) state_hash_kernel(SoAView v, unsigned long long* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long h = 0;
+    if (i < v.n) {
+        h = mix64(((unsigned long long)(unsigned)v.id[i] + 1ull) * 0x9E3779B97F4A7C15ull);
+        h = mix64(h ^ (unsigned long long)__double_as_longlong(v.x[i]));
+        h = mix64(h ^ (unsigned long long)__double_as_longlong(v.y[i]));
+        h = mix64(h ^ (unsigned long long)__double_as_longlong(v.vx[i]));
+        h = mix64(h ^ (unsigned long long)__double_as_longlong(v.vy[i]));
+    }
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
 }
 
 struct StatsPartial {
@@ -181,6 +211,16 @@ static bool pointer_on_device(const void* p) {
         return false;
     }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// A pinned (page-locked, mapped) host array can be written by a kernel directly: returns the device alias of p, or null.
+static void* device_alias_of_host(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 static int view_of(psim_sim* sim, SoAView* v, bool* have_acc) {
@@ -349,6 +389,16 @@ int psim_host_unregister(void* host_ptr) {
     return PSIM_OK;
 }
 
+int psim_device_count(int* count) {
+    if (!count) return fail(PSIM_ERR_INVALID, "psim_device_count: NULL");
+    *count = 0;
+    if (cudaGetDeviceCount(count) != cudaSuccess || *count == 0) {
+        cudaGetLastError();
+        return fail(PSIM_ERR_NO_DEVICE, "psim_device_count: no CUDA device visible; libpsim has no CPU fallback");
+    }
+    return PSIM_OK;
+}
+
 int psim_device_init(int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -413,6 +463,7 @@ int psim_create(psim_sim** out, const psim_config* cfg_in, const particle_t* par
         return bail(fail(PSIM_ERR_CUDA, "psim_create: error-word allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
 
     const bool on_device = num_parts > 0 && pointer_on_device(parts);
+    sim->input_on_device = on_device;
     int engine = cfg.engine;
     if (engine != PSIM_ENGINE_AUTO && engine != PSIM_ENGINE_CELLSORT && engine != PSIM_ENGINE_TILED && engine != PSIM_ENGINE_KSTEP)
         return bail(fail(PSIM_ERR_INVALID, "psim_create: unknown engine %d", engine));
@@ -522,6 +573,17 @@ int psim_read_particles(psim_sim* sim, particle_t* dst) {
         PSIM_CUDA(cudaStreamSynchronize(s));
         return PSIM_OK;
     }
+    if ((sim->engine == PSIM_ENGINE_TILED || sim->engine == PSIM_ENGINE_KSTEP) && sim->nranks > 1) {
+        // a slab writes only the records it owns (the analogue of the reference's gather_for_save, part2/mpi.cpp:371-402):
+        // straight from the stripes into the caller's array, in original order -- a device array, or a pinned host array
+        // through its device alias (zero-copy scatter over PCIe: no staging buffer, no host loop)
+        particle_t* d = pointer_on_device(dst) ? dst : static_cast<particle_t*>(device_alias_of_host(dst));
+        if (d) {
+            PSIM_TRY(engine_writeback(sim, d, nullptr));
+            PSIM_CUDA(cudaStreamSynchronize(sim->stream));
+            return PSIM_OK;
+        }
+    }
     SoAView v;
     bool acc;
     PSIM_TRY(view_of(sim, &v, &acc));
@@ -547,12 +609,30 @@ int psim_read_particles(psim_sim* sim, particle_t* dst) {
         PSIM_TRY(ensure_scratch(sim, sizeof(particle_t) * (size_t)std::max(v.n, 1), reinterpret_cast<void**>(&stage)));
         if (v.n) soa_pack_kernel<<<blocks, kObsThreads, 0, s>>>(v, acc, stage);
         ++sim->launches;
-        std::vector<particle_t> rec((size_t)v.n);
-        std::vector<int> ids((size_t)v.n);
-        PSIM_CUDA(cudaMemcpyAsync(rec.data(), stage, sizeof(particle_t) * (size_t)v.n, cudaMemcpyDeviceToHost, s));
-        PSIM_CUDA(cudaMemcpyAsync(ids.data(), v.id, sizeof(int) * (size_t)v.n, cudaMemcpyDeviceToHost, s));
-        PSIM_CUDA(cudaStreamSynchronize(s));
-        for (int i = 0; i < v.n; ++i) dst[ids[i]] = rec[i];
+        // pageable destination: pinned staging for the packed records and their ids, then the host places them
+        particle_t* h_rec = nullptr;
+        int* h_ids = nullptr;
+        PSIM_CUDA(cudaMallocHost(&h_rec, sizeof(particle_t) * (size_t)std::max(v.n, 1)));
+        if (cudaMallocHost(&h_ids, sizeof(int) * (size_t)std::max(v.n, 1)) != cudaSuccess) {
+            cudaFreeHost(h_rec);
+            return fail(PSIM_ERR_CUDA, "psim_read_particles: pinned staging: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        cudaError_t ce = cudaMemcpyAsync(h_rec, stage, sizeof(particle_t) * (size_t)v.n, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_ids, v.id, sizeof(int) * (size_t)v.n, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce == cudaSuccess) {
+            const int nthreads = std::max(1, std::min(8, v.n / (1 << 18)));
+            std::vector<std::thread> pool;
+            for (int w = 0; w < nthreads; ++w)
+                pool.emplace_back([=]() {
+                    const long long lo = (long long)v.n * w / nthreads, hi = (long long)v.n * (w + 1) / nthreads;
+                    for (long long i = lo; i < hi; ++i) dst[h_ids[i]] = h_rec[i];
+                });
+            for (auto& t : pool) t.join();
+        }
+        cudaFreeHost(h_rec);
+        cudaFreeHost(h_ids);
+        if (ce != cudaSuccess) return fail(PSIM_ERR_CUDA, "psim_read_particles: %s", cudaGetErrorString(ce));
     }
     return PSIM_OK;
 }
@@ -574,6 +654,14 @@ int psim_read_positions(psim_sim* sim, double* xy) {
         PSIM_CUDA(cudaMemcpyAsync(xy, stage, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
         PSIM_CUDA(cudaStreamSynchronize(s));
         return PSIM_OK;
+    }
+    if ((sim->engine == PSIM_ENGINE_TILED || sim->engine == PSIM_ENGINE_KSTEP) && sim->nranks > 1) {
+        double2* d = pointer_on_device(xy) ? reinterpret_cast<double2*>(xy) : static_cast<double2*>(device_alias_of_host(xy));
+        if (d) {
+            PSIM_TRY(engine_writeback(sim, nullptr, d));
+            PSIM_CUDA(cudaStreamSynchronize(sim->stream));
+            return PSIM_OK;
+        }
     }
     SoAView v;
     bool acc;
@@ -718,6 +806,84 @@ int psim_stats(psim_sim* sim, psim_stats_t* out) {
     return PSIM_OK;
 }
 
+int psim_gather(psim_sim* sim, particle_t* dst, int root) {
+    if (!sim) return fail(PSIM_ERR_INVALID, "psim_gather: NULL handle");
+    if (root < 0 || root >= sim->nranks) return fail(PSIM_ERR_INVALID, "psim_gather: root %d of %d", root, sim->nranks);
+    if (sim->rank == root && !dst) return fail(PSIM_ERR_INVALID, "psim_gather: the root needs a destination");
+    if (sim->nranks == 1) return psim_read_particles(sim, dst);
+    DeviceGuard g(sim->device);
+    PSIM_TRY(check_device_error(sim));
+    SoAView v;
+    bool acc;
+    PSIM_TRY(view_of(sim, &v, &acc));
+    cudaStream_t s = sim->stream;
+    std::vector<int> counts((size_t)sim->nranks);
+    PSIM_TRY(comm_allgather_counts(sim, v.n, counts.data(), s));
+    long long total = 0;
+    for (int c : counts) total += c;
+    if (total != sim->n_total) return fail(PSIM_ERR_STATE, "psim_gather: the slabs own %lld particles, expected %d", total, sim->n_total);
+    const bool is_root = sim->rank == root;
+    DeviceArena tmp;
+    particle_t *rec = nullptr, *out = nullptr;
+    int* ids = nullptr;
+    // root: room for everybody's records (its own block at its offset); others: their own block
+    const size_t cap = is_root ? (size_t)sim->n_total : (size_t)std::max(v.n, 1);
+    int st = tmp.alloc(&rec, cap);
+    if (st == PSIM_OK) st = tmp.alloc(&ids, cap);
+    size_t my_off = 0;
+    if (is_root)
+        for (int r = 0; r < root; ++r) my_off += (size_t)counts[r];
+    if (st == PSIM_OK && v.n) {
+        soa_pack_kernel<<<(v.n + kObsThreads - 1) / kObsThreads, kObsThreads, 0, s>>>(v, acc, rec + my_off);
+        ++sim->launches;
+        if (cudaMemcpyAsync(ids + my_off, v.id, sizeof(int) * (size_t)v.n, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            st = fail(PSIM_ERR_CUDA, "psim_gather: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (st == PSIM_OK) st = comm_gather_records(sim, root, rec, ids, v.n, sizeof(particle_t), rec, ids, counts.data(), s);
+    if (st == PSIM_OK && is_root) {
+        const bool on_dev = pointer_on_device(dst);
+        out = dst;
+        if (!on_dev) st = tmp.alloc(&out, (size_t)sim->n_total);
+        if (st == PSIM_OK) {
+            const long long threads = 3ll * sim->n_total;
+            place_records_kernel<<<(unsigned)((threads + kObsThreads - 1) / kObsThreads), kObsThreads, 0, s>>>(rec, ids, sim->n_total, out);
+            ++sim->launches;
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess && !on_dev) e = cudaMemcpyAsync(dst, out, sizeof(particle_t) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) st = fail(PSIM_ERR_CUDA, "psim_gather: %s", cudaGetErrorString(e));
+        }
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess && st == PSIM_OK) st = fail(PSIM_ERR_CUDA, "psim_gather: %s", cudaGetErrorString(cudaGetLastError()));
+    tmp.release();
+    return st;
+}
+
+int psim_state_hash(psim_sim* sim, unsigned long long* out, long long* owned) {
+    if (!sim || !out) return fail(PSIM_ERR_INVALID, "psim_state_hash: NULL argument");
+    DeviceGuard g(sim->device);
+    PSIM_TRY(check_device_error(sim));
+    SoAView v;
+    bool acc;
+    PSIM_TRY(view_of(sim, &v, &acc));
+    cudaStream_t s = sim->stream;
+    DeviceArena tmp;
+    unsigned long long* d = nullptr;
+    PSIM_TRY(tmp.alloc(&d, 1));
+    int st = PSIM_OK;
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), s);
+    if (e == cudaSuccess && v.n) {
+        state_hash_kernel<<<(v.n + kObsThreads - 1) / kObsThreads, kObsThreads, 0, s>>>(v, d);
+        ++sim->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) st = fail(PSIM_ERR_CUDA, "psim_state_hash: %s", cudaGetErrorString(e));
+    tmp.release();
+    if (owned) *owned = v.n;
+    return st;
+}
+
 int psim_info(psim_sim* sim, psim_info_t* out) {
     if (!sim || !out) return fail(PSIM_ERR_INVALID, "psim_info: NULL argument");
     std::memset(out, 0, sizeof *out);
@@ -732,6 +898,7 @@ int psim_info(psim_sim* sim, psim_info_t* out) {
     out->kernel_launches = sim->launches;
     out->num_parts = sim->n_total;
     out->engine_switches = sim->engine_switches;
+    out->input_on_device = sim->input_on_device ? 1 : 0;
     out->device_bytes = (long long)sim->mem.bytes + cellsort_bytes(sim) + tiled_bytes(sim) + kstep_bytes(sim);
     if (sim->engine == PSIM_ENGINE_KSTEP) {
         kstep_info(sim, out);

@@ -132,6 +132,51 @@ int kstep_exchange(psim_sim* sim, int parity, cudaStream_t s) {
     return PSIM_OK;
 }
 
+// ---- gather to one rank (the reference's gather_for_save, part2/mpi.cpp:371-402) ------------------------------------------
+// counts[r] = number of records rank r owns (sum-allreduce of a vector in which every rank fills only its own slot)
+int comm_allgather_counts(psim_sim* sim, int mine, int* counts_host, cudaStream_t s) {
+    for (int r = 0; r < sim->nranks; ++r) counts_host[r] = r == sim->rank ? mine : 0;
+    if (sim->nranks == 1) return PSIM_OK;
+    if (!sim->comm) return fail(PSIM_ERR_STATE, "slab %d/%d is not connected: call psim_comm_connect first", sim->rank, sim->nranks);
+    ncclComm_t comm = static_cast<ncclComm_t>(sim->comm);
+    int* d = nullptr;
+    PSIM_CUDA(cudaMalloc(&d, sizeof(int) * (size_t)sim->nranks));
+    cudaError_t e = cudaMemcpyAsync(d, counts_host, sizeof(int) * (size_t)sim->nranks, cudaMemcpyHostToDevice, s);
+    ncclResult_t r = e == cudaSuccess ? g_nccl.AllReduce(d, d, (size_t)sim->nranks, ncclInt32, ncclSum, comm, s) : ncclSuccess;
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(counts_host, d, sizeof(int) * (size_t)sim->nranks, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (r != ncclSuccess) return fail(PSIM_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    if (e != cudaSuccess) return fail(PSIM_ERR_CUDA, "comm_allgather_counts: %s", cudaGetErrorString(e));
+    return PSIM_OK;
+}
+
+// Every rank but `root` sends its `mine` packed records (device) + ids (device); root receives rank r's block at offset
+// offs[r] of rec_all / id_all (device arrays sized for all particles).  One NCCL group.
+int comm_gather_records(psim_sim* sim, int root, const void* rec, const int* ids, int mine, size_t rec_bytes, void* rec_all, int* id_all,
+                        const int* counts, cudaStream_t s) {
+    if (sim->nranks == 1) return PSIM_OK;
+    ncclComm_t comm = static_cast<ncclComm_t>(sim->comm);
+    PSIM_NCCL(g_nccl.GroupStart());
+    if (sim->rank != root) {
+        if (mine > 0) {
+            PSIM_NCCL(g_nccl.Send(rec, (size_t)mine * rec_bytes, ncclInt8, root, comm, s));
+            PSIM_NCCL(g_nccl.Send(ids, (size_t)mine * sizeof(int), ncclInt8, root, comm, s));
+        }
+    } else {
+        size_t off = 0;
+        for (int r = 0; r < sim->nranks; ++r) {
+            if (r != root && counts[r] > 0) {
+                PSIM_NCCL(g_nccl.Recv(static_cast<char*>(rec_all) + off * rec_bytes, (size_t)counts[r] * rec_bytes, ncclInt8, r, comm, s));
+                PSIM_NCCL(g_nccl.Recv(id_all + off, (size_t)counts[r] * sizeof(int), ncclInt8, r, comm, s));
+            }
+            off += (size_t)counts[r];
+        }
+    }
+    PSIM_NCCL(g_nccl.GroupEnd());
+    return PSIM_OK;
+}
+
 // ---- peer-memory exchange ----------------------------------------------------------------------------
 // Each slab maps its neighbours' export buffers and flag words (CUDA IPC; the 64-byte handles travel through the
 // NCCL communicator once at connect time).  Per step: the kernel stores its boundary rows' exports into the

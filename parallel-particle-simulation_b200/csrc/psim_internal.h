@@ -133,6 +133,7 @@ struct psim_sim {
     int row_begin = 0, row_end = 0;
     long long steps_done = 0;
     long long launches = 0;
+    bool input_on_device = false;
     int engine_switches = 0;  // kstep -> cellsort hand-overs after an unrecoverable capacity / speed failure
     int* d_err = nullptr;  // device error word
     int* h_err = nullptr;  // pinned mirror
@@ -175,6 +176,9 @@ int tiled_exchange(psim_sim* sim, int parity, cudaStream_t s);  // psim_comm.cpp
 void tiled_boundary_rows(psim_sim* sim, int parity, char** first_owned, char** last_owned, char** ghost_lo, char** ghost_hi,
                          size_t* row_bytes);
 void comm_destroy(psim_sim* sim);
+int comm_allgather_counts(psim_sim* sim, int mine, int* counts_host, cudaStream_t s);
+int comm_gather_records(psim_sim* sim, int root, const void* rec, const int* ids, int mine, size_t rec_bytes, void* rec_all, int* id_all,
+                        const int* counts, cudaStream_t s);
 int comm_p2p_wait(psim_sim* sim, cudaStream_t s);     // stream waits until both neighbours have finished step p2p_steps
 int comm_p2p_signal(psim_sim* sim, cudaStream_t s);   // tell both neighbours that my step ++p2p_steps is finished
 void tiled_export_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, size_t* row_bytes, int* lrows, int* ntx);

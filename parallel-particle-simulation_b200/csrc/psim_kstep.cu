@@ -48,6 +48,7 @@
 //            offsets become the tile's new header, and pos / vel / id (/ acc) are stored to the other parity.  Tiles
 //            of a slab's first / last row also store their facing band straight into the neighbour GPU's ghost row.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -799,16 +800,16 @@ __global__ void __launch_bounds__(128) kstep_writeback_kernel(const double2* __r
     const int lt = (1 + blockIdx.x / ntx) * ntx + blockIdx.x % ntx;
     const int n = min(hdr[(size_t)lt * kHdrInts + 9], cap);
     const size_t gbase = (size_t)lt * cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int id = sid[gbase + i];
-        const double2 p = pos[gbase + i];
-        if (out_xy) {
-            out_xy[id] = p;
-        } else {
-            double2* q = reinterpret_cast<double2*>(out + id);
-            q[0] = p;
-            q[1] = vel[gbase + i];
-            q[2] = have_acc ? acc[gbase + i] : make_double2(0.0, 0.0);
+    if (out_xy) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) out_xy[sid[gbase + i]] = pos[gbase + i];
+    } else {
+        // three adjacent lanes write the three 16-byte pieces of one 48-byte record: one contiguous transaction per record
+        // (this matters when `out` is pinned host memory written over PCIe)
+        for (int u = threadIdx.x; u < 3 * n; u += blockDim.x) {
+            const int i = u / 3, piece = u - 3 * i;
+            const int id = sid[gbase + i];
+            const double2 v = piece == 0 ? pos[gbase + i] : piece == 1 ? vel[gbase + i] : (have_acc ? acc[gbase + i] : make_double2(0.0, 0.0));
+            reinterpret_cast<double2*>(out + id)[piece] = v;
         }
     }
 }
@@ -927,6 +928,7 @@ static int klaunch_rows(psim_sim* sim, KstepEngine* e, int parity_in, int nsub, 
     P.lrow0 = lrow0;
     P.row_stride = row_stride;
     P.ntiles = nrows * e->ntx;
+    if (allow_peer && sim->nranks > 1) P.acc_tmp += (size_t)e->grid_cap * e->nmax;   // the boundary launch's own scratch
     P.nsub = nsub;
     P.seq = seq;
     // displacement bound per step that H halo cells allow for nsub fused steps, with a 2 % margin for the rounding of the
@@ -982,6 +984,16 @@ int kstep_default_tile(int bincnt) {
 int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts, int n, bool parts_on_device, bool* unsuitable) {
     *unsuitable = false;
     cudaStream_t s = sim->stream;
+    static const bool trace = std::getenv("PSIM_TRACE") != nullptr;   // phase wall times of create on stderr
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        const double t = now();
+        std::fprintf(stderr, "[psim trace] kstep_create rank %d: %-28s %8.3f ms\n", sim->rank, what, 1e3 * (t - t_prev));
+        t_prev = t;
+    };
     int ts = cfg->tile_cells;
     if (ts == 0) ts = kstep_default_tile(sim->bincnt);
     if (ts != 16 && ts != 32 && ts != 64) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32 or 64 (got %d)", ts);
@@ -1022,9 +1034,10 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
         PSIM_CUDA(cudaMemsetAsync(e->hdr[b], 0, tiles * kHdrInts * sizeof(int), s));
     }
     PSIM_TRY(e->mem.alloc(&e->acc, slots));
-    PSIM_TRY(e->mem.alloc(&e->acc_tmp, (size_t)e->grid_cap * e->nmax));
+    PSIM_TRY(e->mem.alloc(&e->acc_tmp, (size_t)2 * e->grid_cap * e->nmax));   // (x2: a slab's boundary and interior launches run concurrently)
     PSIM_TRY(e->mem.alloc(&e->tcount, tiles));
     PSIM_CUDA(cudaMemsetAsync(e->tcount, 0, sizeof(int) * tiles, s));
+    lap("configure + allocate");
     // fill: device input is read in place; host input is streamed through a bounded staging buffer
     {
         DeviceArena stage;
@@ -1047,6 +1060,7 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
         if (!parts_on_device) PSIM_CUDA(cudaStreamSynchronize(s));   // the staging buffer is freed below
         stage.release();
     }
+    lap("upload + fill");
     // suitability: the densest tile must leave headroom for fluctuations, else the caller falls back
     {
         std::vector<int> h(tiles);
@@ -1068,6 +1082,7 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     // partition the stripes into classes: a 0-step launch from parity 0 into parity 1
     PSIM_TRY(klaunch_rows(sim, e, 0, 0, true, e->seq++, 1, e->lrows, 1, false, s));
     PSIM_CUDA(cudaGetLastError());
+    lap("suitability + partition");
     e->parity = 1;
     e->acc_valid = true;   // zeros
     return PSIM_OK;

@@ -9,16 +9,23 @@
 //   * part3/main.cu                   -- device pointer (cudaMalloc'ed AoS), one calling thread
 //
 // Observable contract: after call k returns, parts[i] holds the state after
-// step k in original order.  The drivers read `parts` only when (k % savefreq) == 0
-// (main.cpp:135-136, main.cu:134-136), so the default policy writes the caller's array back on
-// exactly those calls and on the last one (k == nsteps-1); PSIM_SYNC=every restores the literal
-// every-call write-back, PSIM_SYNC=final only the last, PSIM_SYNC=none never.
+// step k in original order.  Policies (PSIM_SYNC):
+//   every  the literal contract: the caller's array is brought up to date on every call.  DEFAULT for a
+//          host array (a caller may look at it after any step).
+//   save   the array is brought up to date on the calls after which the reference drivers read it --
+//          (k % savefreq) == 0 (main.cpp:135-136, main.cu:134-136) and k == nsteps-1 -- and the steps in
+//          between are only counted and enqueued in batches, which lets the kstep engine fuse them
+//          (psim_step(n) is bit-identical to n calls of psim_step(1)).  DEFAULT for a device array: the
+//          reference CUDA driver cannot observe it without the cudaMemcpy it issues on exactly those steps.
+//   final  only k == nsteps-1;   none  never (timing experiments).
+// Device errors are checked whenever steps are flushed; pending steps are flushed at the latest every
+// PSIM_FLUSH (default 30) calls, so a failure surfaces within that many steps of where it happened.
 //
 // Errors: the reference has no error channel; its CUDA part prints "GPUassert: <msg> <file> <line>"
 // to stderr and exits (part3/gpu.cu:70-77).  Any non-zero libpsim status does the same here.
 //
-// Environment: PSIM_ENGINE=auto|cellsort|tiled  PSIM_TILE=16|32|64  PSIM_DEVICE=<ordinal>
-//              PSIM_SYNC=save|every|final|none   PSIM_VERBOSE=1
+// Environment: PSIM_ENGINE=auto|kstep|tiled|cellsort  PSIM_TILE=16|32|64  PSIM_DEVICE=<ordinal>
+//              PSIM_SYNC=every|save|final|none   PSIM_FLUSH=<calls>   PSIM_VERBOSE=1
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +36,8 @@ namespace {
 
 psim_sim* g_sim = nullptr;
 long long g_call = 0;
+int g_pending = 0;       // steps counted but not yet enqueued
+int g_flush_every = 30;
 enum Policy { kSave, kEvery, kFinal, kNone } g_policy = kSave;
 
 [[noreturn]] void die(int status, const char* file, int line) {
@@ -55,8 +64,13 @@ void step_once(particle_t* parts) {
         case kFinal: materialise = k == PSIM_NSTEPS - 1; break;
         case kNone: break;
     }
-    SHIM_CHECK(psim_step(g_sim, 1, materialise ? PSIM_STEP_DEFAULT : PSIM_STEP_ACCEL_NONE));
-    if (materialise) SHIM_CHECK(psim_read_particles(g_sim, parts));
+    ++g_pending;
+    if (materialise || g_pending >= g_flush_every || k == PSIM_NSTEPS - 1) {
+        SHIM_CHECK(psim_step(g_sim, g_pending, materialise ? PSIM_STEP_DEFAULT : PSIM_STEP_ACCEL_NONE));
+        g_pending = 0;
+        if (materialise) SHIM_CHECK(psim_read_particles(g_sim, parts));   // (checks the device error words first)
+        else SHIM_CHECK(psim_sync(g_sim));
+    }
 }
 
 }  // namespace
@@ -72,29 +86,36 @@ void init_simulation(particle_t* parts, int num_parts, double size) {
     if (const char* e = std::getenv("PSIM_ENGINE")) {
         if (!std::strcmp(e, "cellsort")) cfg.engine = PSIM_ENGINE_CELLSORT;
         else if (!std::strcmp(e, "tiled")) cfg.engine = PSIM_ENGINE_TILED;
+        else if (!std::strcmp(e, "kstep")) cfg.engine = PSIM_ENGINE_KSTEP;
     }
     cfg.tile_cells = env_int("PSIM_TILE", 0);
     cfg.device = env_int("PSIM_DEVICE", -1);
-    if (const char* p = std::getenv("PSIM_SYNC")) {
-        if (!std::strcmp(p, "every")) g_policy = kEvery;
-        else if (!std::strcmp(p, "final")) g_policy = kFinal;
-        else if (!std::strcmp(p, "none")) g_policy = kNone;
-        else g_policy = kSave;
-    }
+    g_flush_every = env_int("PSIM_FLUSH", 30);
+    if (g_flush_every < 1) g_flush_every = 1;
     if (g_sim) {
         psim_destroy(g_sim);
         g_sim = nullptr;
     }
     g_call = 0;
+    g_pending = 0;
     SHIM_CHECK(psim_create(&g_sim, &cfg, parts, num_parts, size));
-    // the drivers read `parts` back every savefreq steps: page-lock it (best effort; a no-op for a device array)
+    psim_info_t info;
+    psim_info(g_sim, &info);
+    g_policy = info.input_on_device ? kSave : kEvery;
+    if (const char* p = std::getenv("PSIM_SYNC")) {
+        if (!std::strcmp(p, "every")) g_policy = kEvery;
+        else if (!std::strcmp(p, "final")) g_policy = kFinal;
+        else if (!std::strcmp(p, "none")) g_policy = kNone;
+        else if (!std::strcmp(p, "save")) g_policy = kSave;
+    }
+    // the drivers read `parts` back: page-lock it (best effort; a no-op for a device array)
     if ((size_t)num_parts * sizeof(particle_t) >= (1u << 20)) (void)psim_host_register(parts, (size_t)num_parts * sizeof(particle_t));
     if (env_int("PSIM_VERBOSE", 0)) {
-        psim_info_t info;
-        psim_info(g_sim, &info);
-        std::fprintf(stderr, "[psim] engine=%s device=%d cells/side=%d tile=%d capacity=%d device_bytes=%lld\n",
-                     info.engine == PSIM_ENGINE_TILED ? "tiled" : "cellsort", info.device, info.bin_count, info.tile_cells,
-                     info.tile_capacity, info.device_bytes);
+        static const char* names[] = {"auto", "cellsort", "tiled", "kstep"};
+        static const char* pol[] = {"save", "every", "final", "none"};
+        std::fprintf(stderr, "[psim] engine=%s device=%d cells/side=%d tile=%d capacity=%d steps/launch=%d sync=%s device_bytes=%lld\n",
+                     names[info.engine & 3], info.device, info.bin_count, info.tile_cells, info.tile_capacity, info.steps_per_launch,
+                     pol[g_policy], info.device_bytes);
     }
 }
 

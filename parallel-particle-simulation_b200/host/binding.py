@@ -30,7 +30,7 @@ DECLARED_SYMBOLS = [
     "psim_error_string", "psim_last_error", "psim_device_init", "psim_host_register", "psim_host_unregister", "psim_config_default", "psim_bin_count", "psim_create",
     "psim_destroy", "psim_step", "psim_sync", "psim_read_particles", "psim_read_positions",
     "psim_read_cells", "psim_read_cell_lists", "psim_stats", "psim_info", "psim_init_particles",
-    "psim_save_frame", "psim_comm_unique_id", "psim_comm_connect", "psim_slab_rows",
+    "psim_save_frame", "psim_comm_unique_id", "psim_comm_connect", "psim_slab_rows", "psim_state_hash", "psim_gather", "psim_device_count",
 ]
 
 
@@ -59,7 +59,7 @@ class Info(C.Structure):
                 ("hw_halo_list", C.c_int), ("hw_tile_population", C.c_int), ("hw_apron", C.c_int),
                 ("outbox_capacity", C.c_int), ("halo_list_capacity", C.c_int), ("reserved_hw_pairs", C.c_int),
                 ("halo_cells", C.c_int), ("steps_per_launch", C.c_int), ("region_capacity", C.c_int),
-                ("recoveries", C.c_int), ("engine_switches", C.c_int)]
+                ("recoveries", C.c_int), ("input_on_device", C.c_int), ("engine_switches", C.c_int)]
 
 
 def lib_path() -> str:
@@ -104,6 +104,8 @@ def lib() -> C.CDLL:
     L.psim_read_cell_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.psim_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.psim_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+    L.psim_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.psim_state_hash.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
     L.psim_init_particles.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
     L.psim_save_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
     L.psim_comm_unique_id.argtypes = [C.c_void_p]
@@ -206,6 +208,17 @@ class Simulation:
         s = Stats()
         _check(lib().psim_stats(self._h, C.byref(s)), "psim_stats")
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def gather(self, out=None, root: int = 0):
+        """collective: rank `root` gets all particles in original order (reference part2 gather_for_save)"""
+        _check(lib().psim_gather(self._h, _address(out) if out is not None else None, root), "psim_gather")
+        return out
+
+    def state_hash(self) -> tuple[int, int]:
+        """(order-independent 64-bit fingerprint of the owned particles, number of owned particles)"""
+        h, n = C.c_ulonglong(), C.c_longlong()
+        _check(lib().psim_state_hash(self._h, C.byref(h), C.byref(n)), "psim_state_hash")
+        return int(h.value), int(n.value)
 
     def info(self) -> dict:
         i = Info()

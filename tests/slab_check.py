@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU slab parity check, one process per GPU:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/slab_check.py [n] [steps] [tile]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/slab_check.py [n] [steps] [tile] [kstep|tiled]
 
 Every rank builds its slab of the same warmed state, all ranks step together (halo exchange + migration over
 NCCL), every rank writes the particles it owns into its copy of the array, the copies are merged on rank 0 and
@@ -27,6 +27,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 120
     tile = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    engine_name = sys.argv[4] if len(sys.argv) > 4 else "kstep"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -34,7 +35,8 @@ def main():
     parts = pkg.init_particles(n, 7)
     orc = Oracle()
     orc.step(parts, size, 40)   # warmed state, identical on every rank
-    sim = pkg.Simulation(parts.copy(), n, size, engine=pkg.ENGINE_TILED, tile_cells=tile, device=local, rank=rank, nranks=world)
+    engine = pkg.ENGINE_KSTEP if engine_name == "kstep" else pkg.ENGINE_TILED
+    sim = pkg.Simulation(parts.copy(), n, size, engine=engine, tile_cells=tile, device=local, rank=rank, nranks=world)
     uid = [pkg.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sim.comm_connect(uid[0])
@@ -61,7 +63,7 @@ def main():
         once = bool((counts == 1).all())
         same = bool(np.array_equal(got, want))
         ok = once and same
-        print(f"SLAB_CHECK {'ok' if ok else 'FAIL'} ranks={world} n={n} steps={done} tile={tile} owned_once={once} "
+        print(f"SLAB_CHECK {'ok' if ok else 'FAIL'} engine={engine_name} ranks={world} n={n} steps={done} tile={tile} owned_once={once} "
               f"bit_identical={same} max_abs_diff={np.abs(got - want).max():.3e} rows={info['row_begin']}..{info['row_end']}", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -252,8 +252,9 @@ def test_device_pointer_flavour(pkg, oracle):
 
 
 # ---------------------------------------------------------------- slabs over several GPUs
+@pytest.mark.parametrize("engine", ["kstep", "tiled"])
 @pytest.mark.parametrize("tile", [16, 32])
-def test_slabs_match_oracle_on_all_visible_gpus(tile):
+def test_slabs_match_oracle_on_all_visible_gpus(tile, engine):
     """One process per GPU (torchrun), halo exchange + migration over NCCL, merged state bit-identical to the oracle."""
     import torch
 
@@ -263,9 +264,37 @@ def test_slabs_match_oracle_on_all_visible_gpus(tile):
     world = min(ngpu, 8)
     n = 60000 if tile == 16 else 400000
     cmd = ["python", "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + tile), os.path.join(os.path.dirname(__file__), "slab_check.py"), str(n), "120", str(tile)]
+           "--master-port", str(29500 + tile + (1 if engine == "tiled" else 0)), os.path.join(os.path.dirname(__file__), "slab_check.py"), str(n), "120", str(tile), engine]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "SLAB_CHECK ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+# ---------------------------------------------------------------- the reference's multi-process flavour
+def _run_mpi_flavour(world, n, steps, port):
+    script = os.path.join(os.path.dirname(__file__), "mpi_flavour_check.py")
+    if world == 1:
+        cmd = ["python", script, str(n), str(steps)]
+    else:
+        cmd = ["python", "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), script, str(n), str(steps)]
+    env = dict(os.environ)
+    env["PSIM_RENDEZVOUS"] = f"/tmp/psim_rendezvous_test_{os.getpid()}_{world}"
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0 and "MPI_FLAVOUR_CHECK ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_mpi_flavour_api_one_rank():
+    """part2/common.h:30-32 through libpsim_mpi_shim.so with num_procs = 1: init / step / gather_for_save vs the oracle."""
+    _run_mpi_flavour(1, 20000, 30, 0)
+
+
+def test_mpi_flavour_api_all_visible_gpus():
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    _run_mpi_flavour(min(ngpu, 8), 400000, 30, 29541)
 
 
 # ---------------------------------------------------------------- drop-in drivers (SURVEY 8b)

@@ -101,6 +101,14 @@ def test_shim_exports_the_reference_mangled_names(pkg):
     assert hasattr(shim, "_Z17simulate_one_stepP10particle_tid")
 
 
+def test_mpi_flavour_shim_exports_the_part2_mangled_names(pkg):
+    """reference part2/common.h:30-32: rank-aware init_simulation / simulate_one_step and gather_for_save (C++ linkage)"""
+    shim = C.CDLL(os.path.join(os.path.dirname(pkg.lib_path()), "libpsim_mpi_shim.so"))
+    for name in ("_Z15init_simulationP10particle_tidii", "_Z17simulate_one_stepP10particle_tidii",
+                 "_Z15gather_for_saveP10particle_tidii"):
+        assert hasattr(shim, name), name
+
+
 def test_no_cpu_fallback_without_a_device(pkg):
     import torch
 
