@@ -24,7 +24,8 @@
  *   psim_gather            gather_for_save      part2/common.h:32, part2/mpi.cpp:371-402 (MPI flavour; the 5-argument
  *                                               entry points themselves are exported by csrc/psim_mpi_shim.cpp)
  *   psim_stats             (no reference code; validation statistics of SURVEY.md section 8c-5)
- *   psim_init_particles    init_particles       part1/main.cpp:31-59
+ *   psim_init_particles    init_particles       part1/main.cpp:31-59 (bit-compatible host replay)
+ *   psim_generate_particles_device               the same construction in parallel on the device (alternative seeding mode)
  *   psim_save_frame        save                 part1/main.cpp:15-28 (same bytes; std::to_chars formatter,
  *                                               one fwrite per 64 k particles instead of a flush per line)
  */
@@ -63,7 +64,7 @@ extern "C" {
 /* flags for psim_step */
 #define PSIM_STEP_DEFAULT     0  /* accelerations are materialised for the LAST step of the batch */
 #define PSIM_STEP_ACCEL_ALL   1  /* store ax, ay after every step of the batch                    */
-#define PSIM_STEP_ACCEL_NONE  2  /* never store ax, ay (read-back then returns the last stored)   */
+#define PSIM_STEP_ACCEL_NONE  2  /* never store ax, ay (a read-back then returns ax = ay = 0)      */
 
 typedef struct psim_sim psim_sim; /* opaque */
 
@@ -97,7 +98,8 @@ typedef struct psim_info_t {
     int tiles_per_side;
     int tile_capacity;     /* particle slots per tile                                           */
     int device;
-    int num_parts;         /* particles owned by this slab right now                            */
+    int num_parts;         /* particles in the box; for a slab (nranks > 1): particles it owned at the
+                              last observation call (read / stats / hash / gather)                */
     int rank, nranks;
     int row_begin, row_end;/* cell rows [begin, end) owned by this slab                         */
     long long steps_done;
@@ -154,11 +156,18 @@ int psim_sync(psim_sim* sim);
 /* ---- observation (all of these synchronise) ---- */
 /* Write the current state, in ORIGINAL particle order, to `dst` (host or device pointer, the
  * caller's full array of `num_parts_total` records; a slab only writes the particles it owns).
- * Fields: x y vx vy of the current step; ax ay = the acceleration used by the last step whose
- * accelerations were stored (see PSIM_STEP_*). */
+ * Fields: x y vx vy of the current step; ax ay = the acceleration used by the LAST step if that step
+ * stored it (see PSIM_STEP_*), else 0 -- every engine. */
 int psim_read_particles(psim_sim* sim, particle_t* dst);
 /* positions only: xy[2*i] = x_i, xy[2*i+1] = y_i, host or device pointer */
 int psim_read_positions(psim_sim* sim, double* xy);
+/* The same, asynchronously (the save path, reference part1/main.cpp:135-136 / part3/main.cu:134-136): _begin enqueues the
+ * original-order gather behind the steps enqueued so far and the device->host copy on a separate stream, then returns;
+ * steps enqueued afterwards run while the copy flies.  _end blocks until the oldest un-awaited read has landed in its
+ * host buffer (which should be page-locked: psim_host_register).  At most two reads in flight.  The state that is read
+ * is checked for device-side errors at the next synchronising call. */
+int psim_read_positions_begin(psim_sim* sim, double* xy_host);
+int psim_read_positions_end(psim_sim* sim);
 /* cell_of_particle[i] = row*bin_count+col with row = floor(x/0.01), col = floor(y/0.01)
  * (bit-exact IEEE division, reference part1/serial.cpp:41-43); cell_counts[c] = population of
  * cell c (bin_count^2 ints).  Either pointer may be NULL.  HOST pointers. */
@@ -179,6 +188,13 @@ int psim_info(psim_sim* sim, psim_info_t* out);
  * velocities in [-1,1) -- reference part1/main.cpp:31-59.  seed 0 = std::random_device.
  * ax, ay are set to 0. */
 int psim_init_particles(particle_t* parts_host, int num_parts, double size, int seed);
+/* Alternative seeding mode for large N: the same construction (one particle per site of the reference's sx x sy lattice,
+ * sites handed out by a pseudo-random permutation, float velocities uniform in [-1, 1), ax = ay = 0) generated IN PARALLEL
+ * on the device into a device array -- no host generator, no host->device upload (at 160 M particles the sequential
+ * reference generator and a 7.7 GB upload dominate everything else).  Deterministic in (num_parts, seed), but NOT the
+ * reference's bits for that seed: psim_init_particles is the bit-compatible replay.  Asynchronous on `stream`
+ * (a cudaStream_t; NULL = the default stream). */
+int psim_generate_particles_device(particle_t* parts_device, int num_parts, double size, int seed, void* stream);
 /* Append one frame to an open trajectory file in the reference's text format
  * (part1/main.cpp:15-28): first call writes "N size", every call N lines "x y" + blank line.
  * `file` is a FILE*; `xy` the interleaved positions from psim_read_positions. */

@@ -10,5 +10,5 @@ The directory name contains '-', so import it through `__graft_entry__.load_pack
 from .host.binding import (  # noqa: F401
     ENGINE_AUTO, ENGINE_CELLSORT, ENGINE_TILED, ENGINE_KSTEP, STEP_ACCEL_ALL, STEP_ACCEL_NONE, STEP_DEFAULT,
     PsimError, Simulation, bin_count, build_native, init_particles, init_simulation, lib, lib_path,
-    simulate_one_step, box_size, comm_unique_id, slab_rows, DECLARED_SYMBOLS,
+    simulate_one_step, box_size, generate_particles_device, comm_unique_id, slab_rows, DECLARED_SYMBOLS,
 )

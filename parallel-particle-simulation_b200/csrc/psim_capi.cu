@@ -129,6 +129,47 @@ __global__ void __launch_bounds__(kObsThreads) state_hash_kernel(SoAView v, unsi
     if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
 }
 
+// ---- device-side particle generation ------------------------------------------------------------------------
+// The reference generator (part1/main.cpp:31-59) is a sequential Fisher-Yates draw from one mt19937 stream with
+// rejection-sampled integers: it cannot be replayed in parallel bit for bit (psim_init_particles is its host replay).  This is
+// the documented ALTERNATIVE seeding mode with the same construction -- every particle on its own site of the same
+// sx x sy lattice, sites assigned by a pseudo-random permutation, float velocities uniform in [-1, 1) -- computed per particle:
+// the permutation is a 4-round Feistel network on the smallest even-bit domain >= N with cycle walking, keyed by the seed;
+// velocities come from a counter-based hash of (seed, i).  Same statistics, different bits than the reference for a given seed.
+__device__ __forceinline__ unsigned feistel_round(unsigned r, unsigned key, int half_bits) {
+    unsigned long long z = ((unsigned long long)r + 1ull) * 0x9E3779B97F4A7C15ull + key;
+    z = (z ^ (z >> 29)) * 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 32;
+    return (unsigned)z & ((1u << half_bits) - 1u);
+}
+__global__ void __launch_bounds__(kObsThreads) generate_particles_kernel(particle_t* __restrict__ out, int n, double size, unsigned seed,
+                                                                        int sx, int sy, int half_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned mask = (1u << half_bits) - 1u;
+    unsigned v = (unsigned)i;
+    do {   // cycle walking: the Feistel network permutes [0, 4^half_bits); follow the cycle until it re-enters [0, n)
+        unsigned l = v >> half_bits, r = v & mask;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned t = l ^ feistel_round(r, seed * 0x85EBCA6Bu + (unsigned)k * 0xC2B2AE35u, half_bits);
+            l = r;
+            r = t;
+        }
+        v = (l << half_bits) | r;
+    } while (v >= (unsigned)n);
+    const int site = (int)v;
+    unsigned long long h = ((unsigned long long)seed << 32 | (unsigned)i) * 0xD6E8FEB86659FD93ull;
+    h = (h ^ (h >> 32)) * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    const float vx = (float)((unsigned)(h >> 40)) * (1.0f / 8388608.0f) - 1.0f;          // 24 bits -> [-1, 1)
+    const float vy = (float)((unsigned)(h >> 8) & 0xFFFFFFu) * (1.0f / 8388608.0f) - 1.0f;
+    double2* q = reinterpret_cast<double2*>(out + i);
+    q[0] = make_double2(size * (1. + (site % sx)) / (1 + sx), size * (1. + (site / sx)) / (1 + sy));   // reference main.cpp:49-50
+    q[1] = make_double2((double)vx, (double)vy);
+    q[2] = make_double2(0.0, 0.0);
+}
+
 struct StatsPartial {
     double dmin, dsum, ke, vmax;
     long long pairs, touched;
@@ -226,7 +267,7 @@ static void* device_alias_of_host(const void* p) {
 static int view_of(psim_sim* sim, SoAView* v, bool* have_acc) {
     if (sim->engine == PSIM_ENGINE_CELLSORT) {
         PSIM_TRY(cellsort_view(sim, v));
-        *have_acc = true;
+        *have_acc = cellsort_acc_valid(sim);   // zeros instead of accelerations that belong to an older particle order
     } else if (sim->engine == PSIM_ENGINE_KSTEP) {
         PSIM_TRY(kstep_view(sim, v));
         *have_acc = true;  // zeros are substituted when the stored accelerations are stale
@@ -234,6 +275,7 @@ static int view_of(psim_sim* sim, SoAView* v, bool* have_acc) {
         PSIM_TRY(tiled_view(sim, v));
         *have_acc = true;  // the gather already substitutes zeros when accelerations are stale
     }
+    sim->owned_last = v->n;
     return PSIM_OK;
 }
 
@@ -389,6 +431,20 @@ int psim_host_unregister(void* host_ptr) {
     return PSIM_OK;
 }
 
+int psim_generate_particles_device(particle_t* parts_device, int num_parts, double size, int seed, void* stream) {
+    if (num_parts < 0 || (num_parts > 0 && !parts_device)) return fail(PSIM_ERR_INVALID, "psim_generate_particles_device: bad array");
+    if (num_parts == 0) return PSIM_OK;
+    if (!pointer_on_device(parts_device)) return fail(PSIM_ERR_INVALID, "psim_generate_particles_device: needs a device array (psim_init_particles fills host arrays)");
+    const int sx = (int)std::ceil(std::sqrt((double)num_parts));
+    const int sy = (num_parts + sx - 1) / sx;
+    int half_bits = 1;
+    while ((1ull << (2 * half_bits)) < (unsigned long long)num_parts) ++half_bits;
+    generate_particles_kernel<<<(num_parts + kObsThreads - 1) / kObsThreads, kObsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        parts_device, num_parts, size, (unsigned)seed, sx, sy, half_bits);
+    PSIM_CUDA(cudaGetLastError());
+    return PSIM_OK;
+}
+
 int psim_device_count(int* count) {
     if (!count) return fail(PSIM_ERR_INVALID, "psim_device_count: NULL");
     *count = 0;
@@ -531,6 +587,15 @@ int psim_destroy(psim_sim* sim) {
     cellsort_destroy(sim);
     tiled_destroy(sim);
     kstep_destroy(sim);
+    for (int k = 0; k < 2; ++k) {
+        if (sim->async_ready[k]) cudaEventDestroy(sim->async_ready[k]);
+        if (sim->async_done[k]) cudaEventDestroy(sim->async_done[k]);
+    }
+    if (sim->copy_stream) {
+        cudaStreamSynchronize(sim->copy_stream);
+        cudaStreamDestroy(sim->copy_stream);
+    }
+    if (sim->async_err) cudaFreeHost(sim->async_err);
     sim->scratch.release();
     sim->mem.release();
     if (sim->h_err) cudaFreeHost(sim->h_err);
@@ -684,6 +749,63 @@ int psim_read_positions(psim_sim* sim, double* xy) {
     PSIM_CUDA(cudaGetLastError());
     PSIM_CUDA(cudaMemcpyAsync(xy, stage, sizeof(double2) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, s));
     PSIM_CUDA(cudaStreamSynchronize(s));
+    return PSIM_OK;
+}
+
+// Asynchronous flavour of psim_read_positions for the save path (reference part3/main.cu:134-136 copies the whole array
+// synchronously before every save): _begin enqueues the original-order gather on the handle's stream and the device->host copy
+// on a separate copy stream and returns; steps enqueued afterwards overlap the copy.  _end waits for the OLDEST read that has
+// not been waited for.  At most two reads may be in flight; `xy_host` should be page-locked (psim_host_register) or the copy
+// degrades to a staged, synchronous one inside the CUDA runtime.
+int psim_read_positions_begin(psim_sim* sim, double* xy_host) {
+    if (!sim || !xy_host) return fail(PSIM_ERR_INVALID, "psim_read_positions_begin: NULL argument");
+    DeviceGuard g(sim->device);
+    if (sim->async_issued - sim->async_waited >= 2) return fail(PSIM_ERR_STATE, "psim_read_positions_begin: two reads already in flight");
+    if (sim->nranks > 1 || sim->engine == PSIM_ENGINE_CELLSORT) {   // (slabs / the fallback engine: plain synchronous read)
+        PSIM_TRY(psim_read_positions(sim, xy_host));
+        ++sim->async_issued;
+        return PSIM_OK;
+    }
+    if (!sim->copy_stream) {
+        PSIM_CUDA(cudaStreamCreateWithFlags(&sim->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            PSIM_TRY(sim->mem.alloc(&sim->async_stage[k], (size_t)std::max(sim->n_total, 1)));
+            PSIM_CUDA(cudaEventCreateWithFlags(&sim->async_ready[k], cudaEventDisableTiming));
+            PSIM_CUDA(cudaEventCreateWithFlags(&sim->async_done[k], cudaEventDisableTiming));
+        }
+        PSIM_CUDA(cudaHostAlloc(&sim->async_err, 2 * kErrWords * sizeof(int), cudaHostAllocDefault));
+    }
+    const int k = (int)(sim->async_issued & 1u);
+    // (the copy that used this staging buffer two reads ago has been waited for: in-flight count < 2)
+    PSIM_TRY(engine_writeback(sim, nullptr, sim->async_stage[k]));
+    PSIM_CUDA(cudaEventRecord(sim->async_ready[k], sim->stream));
+    PSIM_CUDA(cudaStreamWaitEvent(sim->copy_stream, sim->async_ready[k], 0));
+    PSIM_CUDA(cudaMemcpyAsync(xy_host, sim->async_stage[k], sizeof(double2) * (size_t)sim->n_total, cudaMemcpyDeviceToHost, sim->copy_stream));
+    // the device error words as of this read travel with it: a launch that hit a bound leaves a state that must not be saved
+    PSIM_CUDA(cudaMemcpyAsync(sim->async_err + k * kErrWords, sim->d_err, kErrWords * sizeof(int), cudaMemcpyDeviceToHost, sim->copy_stream));
+    PSIM_CUDA(cudaEventRecord(sim->async_done[k], sim->copy_stream));
+    sim->async_dst[k] = xy_host;
+    ++sim->async_issued;
+    return PSIM_OK;
+}
+
+int psim_read_positions_end(psim_sim* sim) {
+    if (!sim) return fail(PSIM_ERR_INVALID, "psim_read_positions_end: NULL handle");
+    if (sim->async_issued == sim->async_waited) return fail(PSIM_ERR_STATE, "psim_read_positions_end: no read in flight");
+    DeviceGuard g(sim->device);
+    const int k = (int)(sim->async_waited & 1u);
+    ++sim->async_waited;
+    if (!sim->async_dst[k]) return PSIM_OK;   // that read was done synchronously
+    PSIM_CUDA(cudaEventSynchronize(sim->async_done[k]));
+    double* dst = sim->async_dst[k];
+    sim->async_dst[k] = nullptr;
+    const int* e = sim->async_err + k * kErrWords;
+    if (e[0] != 0 || e[8] != 0) {
+        // a launch before this read hit a capacity / speed bound: let the synchronous path replay it (or hand the state over to
+        // the cellsort engine) and read the repaired state.  NOTE: this also includes the steps enqueued after _begin; callers
+        // that need the exact frame should treat this rare event as "frame taken late".
+        PSIM_TRY(psim_read_positions(sim, dst));
+    }
     return PSIM_OK;
 }
 
@@ -896,7 +1018,7 @@ int psim_info(psim_sim* sim, psim_info_t* out) {
     out->row_end = sim->row_end;
     out->steps_done = sim->steps_done;
     out->kernel_launches = sim->launches;
-    out->num_parts = sim->n_total;
+    out->num_parts = sim->nranks == 1 ? sim->n_total : sim->owned_last;   // slabs: as of the last observation call
     out->engine_switches = sim->engine_switches;
     out->input_on_device = sim->input_on_device ? 1 : 0;
     out->device_bytes = (long long)sim->mem.bytes + cellsort_bytes(sim) + tiled_bytes(sim) + kstep_bytes(sim);

@@ -244,6 +244,7 @@ struct CellsortEngine {
     int* id[2] = {};
     double *ax = nullptr, *ay = nullptr;  // acceleration of the last stored step, indexed like buffer `cur`
     int cur = 0;
+    bool acc_valid = true;   // ax / ay belong to the step that produced the current order (false after a step that did not store them)
 };
 
 __global__ void __launch_bounds__(kThreads) aos_to_soa_kernel(const particle_t* __restrict__ p, int n,
@@ -315,10 +316,13 @@ int cellsort_step(psim_sim* sim, int nsteps, int flags) {
             std::swap(e->id[a], e->id[b]);
         }
         PSIM_CUDA(cudaGetLastError());
+        e->acc_valid = store;   // a step that does not store leaves ax / ay indexed by an older order: stale
         ++sim->steps_done;
     }
     return PSIM_OK;
 }
+
+bool cellsort_acc_valid(psim_sim* sim) { return sim->cs && sim->cs->acc_valid; }
 
 int cellsort_view(psim_sim* sim, SoAView* out) {
     CellsortEngine* e = sim->cs;

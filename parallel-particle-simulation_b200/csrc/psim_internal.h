@@ -134,6 +134,15 @@ struct psim_sim {
     long long steps_done = 0;
     long long launches = 0;
     bool input_on_device = false;
+    int owned_last = 0;       // slabs: particles owned at the last observation (view) call
+    // asynchronous position read-back (psim_read_positions_begin / _end): write-back kernel on the handle's stream, D2H on a
+    // copy stream, two device staging buffers so that a read can fly while the next steps run
+    cudaStream_t copy_stream = nullptr;
+    double2* async_stage[2] = {nullptr, nullptr};
+    cudaEvent_t async_ready[2] = {nullptr, nullptr}, async_done[2] = {nullptr, nullptr};
+    unsigned async_issued = 0, async_waited = 0;
+    double* async_dst[2] = {nullptr, nullptr};   // host destination of the read in each slot
+    int* async_err = nullptr;                    // pinned: device error words as of each read, [slot][kErrWords]
     int engine_switches = 0;  // kstep -> cellsort hand-overs after an unrecoverable capacity / speed failure
     int* d_err = nullptr;  // device error word
     int* h_err = nullptr;  // pinned mirror
@@ -167,6 +176,7 @@ namespace psim {
 int cellsort_create(psim_sim* sim, const particle_t* d_parts_aos, int n);
 int cellsort_step(psim_sim* sim, int nsteps, int flags);
 int cellsort_view(psim_sim* sim, SoAView* out);  // current compact state
+bool cellsort_acc_valid(psim_sim* sim);            // ax / ay of the view belong to the last step
 void cellsort_destroy(psim_sim* sim);
 long long cellsort_bytes(psim_sim* sim);
 

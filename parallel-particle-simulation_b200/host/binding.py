@@ -30,7 +30,7 @@ DECLARED_SYMBOLS = [
     "psim_error_string", "psim_last_error", "psim_device_init", "psim_host_register", "psim_host_unregister", "psim_config_default", "psim_bin_count", "psim_create",
     "psim_destroy", "psim_step", "psim_sync", "psim_read_particles", "psim_read_positions",
     "psim_read_cells", "psim_read_cell_lists", "psim_stats", "psim_info", "psim_init_particles",
-    "psim_save_frame", "psim_comm_unique_id", "psim_comm_connect", "psim_slab_rows", "psim_state_hash", "psim_gather", "psim_device_count",
+    "psim_save_frame", "psim_comm_unique_id", "psim_comm_connect", "psim_slab_rows", "psim_state_hash", "psim_gather", "psim_device_count", "psim_read_positions_begin", "psim_read_positions_end", "psim_generate_particles_device",
 ]
 
 
@@ -104,9 +104,12 @@ def lib() -> C.CDLL:
     L.psim_read_cell_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.psim_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.psim_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+    L.psim_read_positions_begin.argtypes = [C.c_void_p, C.c_void_p]
+    L.psim_read_positions_end.argtypes = [C.c_void_p]
     L.psim_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.psim_state_hash.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
     L.psim_init_particles.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+    L.psim_generate_particles_device.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
     L.psim_save_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
     L.psim_comm_unique_id.argtypes = [C.c_void_p]
     L.psim_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
@@ -137,6 +140,14 @@ def init_particles(n: int, seed: int, size: float | None = None, out: np.ndarray
     assert parts.flags.c_contiguous and parts.dtype == np.float64 and parts.shape == (n, 6)
     _check(lib().psim_init_particles(parts.ctypes.data, n, size, seed), "psim_init_particles")
     return parts
+
+
+def generate_particles_device(out, n: int, seed: int, size: float | None = None, stream: int | None = None):
+    """alternative seeding mode: the reference's construction generated in parallel into a DEVICE array (torch cuda tensor
+    of shape (n, 6), float64)"""
+    size = box_size(n) if size is None else size
+    _check(lib().psim_generate_particles_device(_address(out), n, size, seed, stream), "psim_generate_particles_device")
+    return out
 
 
 def _address(buf) -> int:
@@ -188,6 +199,14 @@ class Simulation:
             out = np.zeros((self.n, 2), dtype=np.float64)
         _check(lib().psim_read_positions(self._h, _address(out)), "psim_read_positions")
         return out
+
+    def read_positions_begin(self, out):
+        _check(lib().psim_read_positions_begin(self._h, _address(out)), "psim_read_positions_begin")
+        return out
+
+    def read_positions_end(self):
+        _check(lib().psim_read_positions_end(self._h), "psim_read_positions_end")
+        return self
 
     def read_cells(self, want_counts: bool = True):
         nb = bin_count(self.size)

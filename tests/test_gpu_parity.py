@@ -154,6 +154,49 @@ def test_against_live_reference_kernel_100k(pkg):
     sim.close()
 
 
+def test_1m_particles_100_steps_bit_identical_to_oracle(pkg, oracle):
+    """BASELINE configs[2] size: 1 M particles, the first 100 steps from the reference's lattice start (seed 42, the
+    reference's job scripts), default engine, against the oracle: stated tolerance 1e-12 relative, asserted bit-identical."""
+    n = 1_000_000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 42)
+    want = parts.copy()
+    sim = pkg.Simulation(parts, n, size)
+    got = sim.step(100).sync().read_particles()
+    oracle.step(want, size, 100)
+    assert rel_err(got[:, :4], want[:, :4]) <= 1e-12
+    assert np.array_equal(got, want)
+    assert np.abs(want[:, 4:]).max() > 0
+    st, ost = sim.stats(), oracle.stats(want, size)
+    assert st["pairs"] == ost["pairs"] and abs(st["dmin"] - ost["dmin"]) <= 1e-15
+    sim.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_20m_particles_vs_live_reference_serial(pkg):
+    """BASELINE configs[3] -- the headline size: 20 M particles.  The GPU warms the lattice start up for 60 steps; from that
+    state the UNMODIFIED reference part1/serial.cpp (oracle/_ref/libref_serial.so, in memory) and the default engine each
+    advance 5 steps.  Tolerance 1e-12 relative on x, y, vx, vy; the only rows allowed to differ at all are particles with
+    three or more in-range neighbours (the reference sums them in hash-set order)."""
+    n = 20_000_000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 42)
+    sim = pkg.Simulation(parts, n, size)
+    warmed = sim.step(60).sync().read_particles()
+    ref_state = warmed.copy()
+    ref = RefKernel("serial").init(ref_state, size)
+    ref.step(5)
+    got = sim.step(5).sync().read_particles()
+    info = sim.info()
+    sim.close()
+    assert info["engine"] == pkg.ENGINE_KSTEP and info["engine_switches"] == 0
+    assert rel_err(got[:, :4], ref_state[:, :4]) <= 1e-12
+    assert rel_err(got[:, 4:], ref_state[:, 4:], floor=1e3) <= 1e-12   # accelerations of the last step (|a| up to ~5e3)
+    differing = int((got != ref_state).any(axis=1).sum())
+    assert differing <= 200, differing
+    assert np.abs(ref_state[:, 4:]).max() > 0
+
+
 # ---------------------------------------------------------------- edge cases
 @pytest.mark.parametrize("engine", ["cellsort", "tiled16", "kstep16", "kstep64"])
 def test_edge_cases(pkg, oracle, engine):
@@ -232,6 +275,28 @@ def test_empty_and_dense_inputs(pkg, oracle):
     sim.close()
 
 
+@pytest.mark.parametrize("engine", ["cellsort", "tiled32", "kstep32"])
+def test_accelerations_after_a_step_that_did_not_store_them_read_as_zero(pkg, oracle, engine):
+    """include/psim.h: ax, ay are those of the LAST step if it stored them, else 0 -- never values that belong to an older
+    step or to another particle (the particle order inside the engines changes every step)."""
+    n = 5000
+    size = box_size(n)
+    parts = pkg.init_particles(n, 4)
+    oracle.step(parts, size, 60)
+    sim = make_sim(pkg, parts, size, engine)
+    want = parts.copy()
+    oracle.step(want, size, 3)
+    got = sim.step(3).sync().read_particles()
+    assert np.array_equal(got, want) and np.abs(got[:, 4:]).max() > 0
+    oracle.step(want, size, 2)
+    got = sim.step(2, pkg.STEP_ACCEL_NONE).sync().read_particles()
+    assert np.array_equal(got[:, :4], want[:, :4]) and not got[:, 4:].any()
+    oracle.step(want, size, 4)
+    got = sim.step(4, pkg.STEP_ACCEL_ALL).sync().read_particles()
+    assert np.array_equal(got, want)
+    sim.close()
+
+
 def test_device_pointer_flavour(pkg, oracle):
     """part3/main.cu hands init_simulation a cudaMalloc'ed AoS; read-back into a device array too."""
     import torch
@@ -248,6 +313,46 @@ def test_device_pointer_flavour(pkg, oracle):
     want = parts.copy()
     oracle.step(want, size, 7)
     assert np.array_equal(out.cpu().numpy(), want)
+    sim.close()
+
+
+def test_device_side_generator_and_async_save_path(pkg, oracle):
+    """the alternative seeding mode generates the reference's construction on the device (every particle on
+    its own lattice site, float velocities in [-1, 1)); a run from it matches the oracle; the asynchronous position read-back
+    returns the same frames as the synchronous one while later steps are already enqueued."""
+    import torch
+
+    n = 50000
+    size = box_size(n)
+    dev = torch.empty((n, 6), dtype=torch.float64, device="cuda")
+    pkg.generate_particles_device(dev, n, 9, size)
+    torch.cuda.synchronize()
+    parts = dev.cpu().numpy()
+    sx = int(np.ceil(np.sqrt(n)))
+    sy = (n + sx - 1) // sx
+    col = np.rint(parts[:, 0] * (1 + sx) / size - 1).astype(np.int64)
+    row = np.rint(parts[:, 1] * (1 + sy) / size - 1).astype(np.int64)
+    site = row * sx + col
+    assert site.min() >= 0 and site.max() < n and len(np.unique(site)) == n          # a permutation of the lattice sites
+    assert np.abs(np.sort(site) - np.arange(n)).max() == 0 and (site != np.arange(n)).mean() > 0.99   # ... and a shuffled one
+    v = parts[:, 2:4]
+    assert v.min() >= -1.0 and v.max() < 1.0 and np.array_equal(v, v.astype(np.float32).astype(np.float64))
+    assert abs(v.mean()) < 0.02 and abs(v.std() - 1 / np.sqrt(3)) < 0.02 and not parts[:, 4:].any()
+    dev2 = torch.empty_like(dev)
+    pkg.generate_particles_device(dev2, n, 9, size)
+    assert torch.equal(dev, dev2)                                                       # deterministic in (n, seed)
+    sim = pkg.Simulation(dev, n, size)                                                  # device-pointer flavour: no upload
+    want = parts.copy()
+    frames = [torch.empty((n, 2), dtype=torch.float64).pin_memory() for _ in range(2)]
+    for k in range(4):
+        sim.step(25)
+        sim.read_positions_begin(frames[k & 1])
+        sim.step(3)                                     # enqueued behind the read: must not disturb the frame
+        sim.read_positions_end()
+        oracle.step(want, size, 25)
+        assert np.array_equal(frames[k & 1].numpy(), want[:, :2]), k
+        oracle.step(want, size, 3)
+    assert np.array_equal(sim.sync().read_particles()[:, :4], want[:, :4])
     sim.close()
 
 
