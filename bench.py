@@ -282,20 +282,25 @@ def main():
             sim2.step(args.steps, pkg.STEP_DEFAULT)
             sim2.sync()
             t3 = time.perf_counter()
-            sim2.read_particles(host)   # every rank: the particles it owns, into its pinned host array
+            if world > 1:
+                sim2.gather(host if rank == 0 else None, root=0)   # rank 0 ends up with ALL particles in original order in its
+            else:                                                  # pinned host array (the reference's gather_for_save)
+                sim2.read_particles(host)
             barrier()
             t4 = time.perf_counter()
             dt = float(allreduce(t4 - t0, dist.ReduceOp.MAX if world > 1 else None))
             e2e_hash, e2e_owned = fingerprint(sim2)
             sim2.close()
             assert e2e_owned == n
-            per_gpu = n / world
             e2e = {"value": n * args.steps / dt, "unit": "particle-steps/s", "seconds": dt,
-                   "h2d_bytes_per_step": 48.0 * n / args.steps, "d2h_bytes_per_step": 48.0 * per_gpu / args.steps,
+                   "h2d_bytes_per_step": 48.0 * n / args.steps, "d2h_bytes_per_step": 48.0 * n / args.steps,
                    "phases_s_rank0": {"create_h2d": t1 - t0, "connect": t2 - t1, "steps": t3 - t2, "read_back_d2h": t4 - t3},
                    "state_hash_after_init_plus_steps": e2e_hash,
-                   "what": "per rank: psim_create(pinned host AoS of ALL particles: H2D + slab filter) + psim_step(K) + "
-                           "psim_read_particles(owned records -> pinned host AoS), wall clock, max over ranks"}
+                   "what": ("psim_create(pinned host AoS, H2D inside) + psim_step(K) + psim_read_particles(-> pinned host AoS, D2H inside), "
+                            "wall clock" if world == 1 else
+                            "every rank: psim_create(the same pinned host AoS) + psim_comm_connect (each rank uploads 1/N of the array, "
+                            "the records reach their slabs over NVLink) + psim_step(K) + psim_gather(all particles, original order -> rank "
+                            "0's pinned host AoS, D2H inside), wall clock, max over ranks")}
 
     if rank != 0:
         if world > 1:

@@ -143,7 +143,12 @@ int  psim_bin_count(double size);
 /* Build the simulation state from `num_parts` AoS records.  `parts` may be a host pointer
  * (part1/main.cpp flavour) or a device pointer (part3/main.cu flavour); the kind is detected.
  * ax, ay of the input are ignored (the reference driver leaves them uninitialised).
- * With nranks > 1 the slab keeps only the particles whose cell row falls in its row range. */
+ * With nranks > 1 the slab keeps only the particles whose cell row falls in its row range.  For a HOST array and
+ * nranks > 1 the upload is cooperative and completes in psim_comm_connect: every rank uploads 1/nranks of the array
+ * (all ranks must be handed the same array, as the reference's driver broadcasts it, part2/main.cpp:150) and the records
+ * travel to their slabs GPU to GPU -- `parts` must stay valid and unchanged until psim_comm_connect has returned, and
+ * capacity errors of the initial tiling are reported there (PSIM_COOP_UPLOAD=0: every rank uploads everything in
+ * psim_create). */
 int psim_create(psim_sim** out, const psim_config* cfg, const particle_t* parts, int num_parts, double size);
 int psim_destroy(psim_sim* sim);
 

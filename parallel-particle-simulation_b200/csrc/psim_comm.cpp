@@ -151,6 +151,57 @@ int comm_allgather_counts(psim_sim* sim, int mine, int* counts_host, cudaStream_
     return PSIM_OK;
 }
 
+// sum-allreduce of a small host vector (in place)
+int comm_allreduce_ints(psim_sim* sim, int* host_values, int count, cudaStream_t s) {
+    if (sim->nranks == 1) return PSIM_OK;
+    if (!sim->comm) return fail(PSIM_ERR_STATE, "slab %d/%d is not connected", sim->rank, sim->nranks);
+    ncclComm_t comm = static_cast<ncclComm_t>(sim->comm);
+    int* d = nullptr;
+    PSIM_CUDA(cudaMalloc(&d, sizeof(int) * (size_t)count));
+    cudaError_t e = cudaMemcpyAsync(d, host_values, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s);
+    ncclResult_t r = e == cudaSuccess ? g_nccl.AllReduce(d, d, (size_t)count, ncclInt32, ncclSum, comm, s) : ncclSuccess;
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(host_values, d, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (r != ncclSuccess) return fail(PSIM_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    if (e != cudaSuccess) return fail(PSIM_ERR_CUDA, "comm_allreduce_ints: %s", cudaGetErrorString(e));
+    return PSIM_OK;
+}
+
+// all-to-all of variable-size record blocks (+ their ids): I send block [send_offs[r], send_offs[r+1]) to rank r and receive
+// count_matrix[src * R + me] records from every src, packed in rank order.  The block for myself is a device copy.
+int comm_alltoall_records(psim_sim* sim, const void* send, const int* send_ids, const int* send_offs, void* recv, int* recv_ids,
+                          const int* count_matrix, size_t rec_bytes, cudaStream_t s) {
+    const int R = sim->nranks, me = sim->rank;
+    ncclComm_t comm = static_cast<ncclComm_t>(sim->comm);
+    size_t roff = 0;
+    PSIM_NCCL(g_nccl.GroupStart());
+    for (int r = 0; r < R; ++r) {
+        const size_t n_in = (size_t)count_matrix[(size_t)r * R + me], n_out = (size_t)(send_offs[r + 1] - send_offs[r]);
+        if (r != me) {
+            if (n_out) {
+                PSIM_NCCL(g_nccl.Send(static_cast<const char*>(send) + (size_t)send_offs[r] * rec_bytes, n_out * rec_bytes, ncclInt8, r, comm, s));
+                PSIM_NCCL(g_nccl.Send(send_ids + send_offs[r], n_out * sizeof(int), ncclInt8, r, comm, s));
+            }
+            if (n_in) {
+                PSIM_NCCL(g_nccl.Recv(static_cast<char*>(recv) + roff * rec_bytes, n_in * rec_bytes, ncclInt8, r, comm, s));
+                PSIM_NCCL(g_nccl.Recv(recv_ids + roff, n_in * sizeof(int), ncclInt8, r, comm, s));
+            }
+        }
+        roff += n_in;
+    }
+    PSIM_NCCL(g_nccl.GroupEnd());
+    roff = 0;
+    for (int r = 0; r < me; ++r) roff += (size_t)count_matrix[(size_t)r * R + me];
+    const size_t n_self = (size_t)(send_offs[me + 1] - send_offs[me]);
+    if (n_self) {
+        PSIM_CUDA(cudaMemcpyAsync(static_cast<char*>(recv) + roff * rec_bytes, static_cast<const char*>(send) + (size_t)send_offs[me] * rec_bytes,
+                                  n_self * rec_bytes, cudaMemcpyDeviceToDevice, s));
+        PSIM_CUDA(cudaMemcpyAsync(recv_ids + roff, send_ids + send_offs[me], n_self * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    }
+    return PSIM_OK;
+}
+
 // Every rank but `root` sends its `mine` packed records (device) + ids (device); root receives rank r's block at offset
 // offs[r] of rec_all / id_all (device arrays sized for all particles).  One NCCL group.
 int comm_gather_records(psim_sim* sim, int root, const void* rec, const int* ids, int mine, size_t rec_bytes, void* rec_all, int* id_all,
@@ -381,6 +432,7 @@ extern "C" int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]) 
     PSIM_CUDA(cudaStreamCreateWithPriority(&sim->comm_stream, cudaStreamNonBlocking, hi));   // exchange first
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_boundary, cudaEventDisableTiming));
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_exchanged, cudaEventDisableTiming));
+    if (kstep_fill_pending(sim)) PSIM_TRY(kstep_distributed_fill(sim));   // cooperative upload: needs the communicator
     if (sim->tiled || sim->kstep) PSIM_TRY(p2p_setup(sim, comm));
     return PSIM_OK;
 }

@@ -755,6 +755,58 @@ __global__ void __launch_bounds__(256) kstep_fill_kernel(const particle_t* __res
     sid[d] = id0 + i;
 }
 
+// ---- cooperative upload (slabs): every rank uploads 1/nranks of the caller's array and the records travel to their slab over
+// NVLink, instead of every rank uploading everything and throwing 1 - 1/nranks of it away ----------------------------------------
+// destination slab of every record of my chunk (+ per-destination counts); tr_bounds[r] = first tile row of rank r, [nranks] = ntx
+__global__ void __launch_bounds__(256) kstep_route_count_kernel(const particle_t* __restrict__ p, int m, int bincnt, int ts, int nranks,
+                                                                const int* __restrict__ tr_bounds, int* __restrict__ dest,
+                                                                int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int tr = axis_cell(p[i].x, bincnt) / ts;
+    int r = 0;
+    while (r + 1 < nranks && tr >= tr_bounds[r + 1]) ++r;
+    dest[i] = r;
+    atomicAdd(counts + r, 1);
+}
+// records grouped by destination: rec = {x y vx vy}, ids = original index
+__global__ void __launch_bounds__(256) kstep_route_pack_kernel(const particle_t* __restrict__ p, int m, int id0, const int* __restrict__ dest,
+                                                               const int* __restrict__ offs, int* __restrict__ cursor,
+                                                               double4* __restrict__ rec, int* __restrict__ ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int r = dest[i];
+    const int d = offs[r] + atomicAdd(cursor + r, 1);
+    const double2* q = reinterpret_cast<const double2*>(p + i);
+    const double2 a = q[0], b = q[1];
+    rec[d] = make_double4(a.x, a.y, b.x, b.y);
+    ids[d] = id0 + i;
+}
+// received records -> tile stripes (the counterpart of kstep_fill_kernel)
+__global__ void __launch_bounds__(256) kstep_fill_records_kernel(const double4* __restrict__ rec, const int* __restrict__ ids, int n, int bincnt,
+                                                                 int ts, int cap, int ntx, int tr_begin, int tr_end, int tr_base,
+                                                                 double2* __restrict__ pos, double2* __restrict__ vel, int* __restrict__ sid,
+                                                                 int* __restrict__ tcount, int* __restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 q = rec[i];
+    const int tr = axis_cell(q.x, bincnt) / ts, tc = axis_cell(q.y, bincnt) / ts;
+    if (tr < tr_begin || tr >= tr_end) {   // routed to the wrong slab: cannot happen, but never write outside my rows
+        atomicOr(err, kErrLostParticle);
+        return;
+    }
+    const int lt = (tr - tr_base) * ntx + tc;
+    const int slot = atomicAdd(tcount + lt, 1);
+    if (slot >= cap) {
+        atomicOr(err, kErrTileOverflow);
+        return;
+    }
+    const size_t d = (size_t)lt * cap + slot;
+    pos[d] = make_double2(q.x, q.y);
+    vel[d] = make_double2(q.z, q.w);
+    sid[d] = ids[i];
+}
+
 // headers of the freshly filled (unpartitioned) stripes: everything counts as class M
 __global__ void __launch_bounds__(256) kstep_hdr_init_kernel(const int* __restrict__ tcount, int ntiles, int cap, int* __restrict__ hdr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -846,6 +898,9 @@ struct KstepEngine {
     int seq = 0;                    // launches issued so far
     std::vector<KLaunchRec> log;    // launches since the last successful synchronisation
     int recoveries = 0;
+    // cooperative upload: the fill is deferred to psim_comm_connect (the caller's host array must stay valid until then)
+    const particle_t* pending_parts = nullptr;
+    int pending_n = 0;
     // gather scratch
     DeviceArena gmem;
     SoAView g{};
@@ -981,6 +1036,8 @@ int kstep_default_tile(int bincnt) {
     return bincnt >= 64 ? 32 : 16;
 }
 
+int kstep_finish_fill(psim_sim* sim, bool* unsuitable);
+
 int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts, int n, bool parts_on_device, bool* unsuitable) {
     *unsuitable = false;
     cudaStream_t s = sim->stream;
@@ -1038,6 +1095,14 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     PSIM_TRY(e->mem.alloc(&e->tcount, tiles));
     PSIM_CUDA(cudaMemsetAsync(e->tcount, 0, sizeof(int) * tiles, s));
     lap("configure + allocate");
+    // Slabs with a host array: by default the upload is cooperative and happens in psim_comm_connect (kstep_distributed_fill)
+    static const bool coop = !(std::getenv("PSIM_COOP_UPLOAD") && std::getenv("PSIM_COOP_UPLOAD")[0] == '0');
+    if (sim->nranks > 1 && !parts_on_device && coop && n > 0) {
+        e->pending_parts = parts;
+        e->pending_n = n;
+        e->parity = 0;
+        return PSIM_OK;
+    }
     // fill: device input is read in place; host input is streamed through a bounded staging buffer
     {
         DeviceArena stage;
@@ -1061,6 +1126,15 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
         stage.release();
     }
     lap("upload + fill");
+    return kstep_finish_fill(sim, unsuitable);
+}
+
+// after the stripes of parity 0 are filled: capacity check, headers, partition launch
+int kstep_finish_fill(psim_sim* sim, bool* unsuitable) {
+    KstepEngine* e = sim->kstep;
+    cudaStream_t s = sim->stream;
+    const int ts = e->ts;
+    const size_t tiles = (size_t)e->lrows_alloc * e->ntx;
     // suitability: the densest tile must leave headroom for fluctuations, else the caller falls back
     {
         std::vector<int> h(tiles);
@@ -1082,13 +1156,83 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     // partition the stripes into classes: a 0-step launch from parity 0 into parity 1
     PSIM_TRY(klaunch_rows(sim, e, 0, 0, true, e->seq++, 1, e->lrows, 1, false, s));
     PSIM_CUDA(cudaGetLastError());
-    lap("suitability + partition");
     e->parity = 1;
     e->acc_valid = true;   // zeros
     return PSIM_OK;
 }
 
 int kstep_exchange(psim_sim* sim, int parity, cudaStream_t s);   // psim_comm.cpp
+
+bool kstep_fill_pending(psim_sim* sim) { return sim->kstep && sim->kstep->pending_parts != nullptr; }
+
+// Cooperative upload, called from psim_comm_connect once the communicator exists: rank r uploads records
+// [r n / nranks, (r+1) n / nranks) of the caller's array (every rank was handed the same array, like the reference's
+// MPI_Bcast, part2/main.cpp:150), routes them by slab on the device and sends every slab its share over NCCL.
+int kstep_distributed_fill(psim_sim* sim) {
+    KstepEngine* e = sim->kstep;
+    cudaStream_t s = sim->stream;
+    const int n = e->pending_n, R = sim->nranks;
+    const particle_t* parts = e->pending_parts;
+    e->pending_parts = nullptr;
+    const int lo = (int)((long long)n * sim->rank / R), hi = (int)((long long)n * (sim->rank + 1) / R), m = hi - lo;
+    DeviceArena tmp;
+    particle_t* d_chunk = nullptr;
+    double4 *d_rec = nullptr, *d_recv = nullptr;
+    int *d_dest = nullptr, *d_ids = nullptr, *d_recv_ids = nullptr, *d_counts = nullptr, *d_bounds = nullptr;
+    std::vector<int> bounds((size_t)R + 1), matrix((size_t)R * R, 0), offs((size_t)R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+        int b, en;
+        tiled_slab_rows(e->ntx, r, R, &b, &en);
+        bounds[(size_t)r] = b;
+        bounds[(size_t)R] = en;
+    }
+    int st = PSIM_OK;
+    auto cuda_ok = [&](cudaError_t err, const char* what) {
+        if (err != cudaSuccess && st == PSIM_OK) st = fail(PSIM_ERR_CUDA, "kstep_distributed_fill: %s: %s", what, cudaGetErrorString(err));
+        return err == cudaSuccess;
+    };
+    if (st == PSIM_OK) st = tmp.alloc(&d_chunk, (size_t)std::max(m, 1));
+    if (st == PSIM_OK) st = tmp.alloc(&d_rec, (size_t)std::max(m, 1));
+    if (st == PSIM_OK) st = tmp.alloc(&d_dest, (size_t)std::max(m, 1));
+    if (st == PSIM_OK) st = tmp.alloc(&d_ids, (size_t)std::max(m, 1));
+    if (st == PSIM_OK) st = tmp.alloc(&d_counts, (size_t)3 * R);   // counts | offsets | cursors
+    if (st == PSIM_OK) st = tmp.alloc(&d_bounds, (size_t)R + 1);
+    if (st == PSIM_OK) {
+        cuda_ok(cudaMemcpyAsync(d_chunk, parts + lo, sizeof(particle_t) * (size_t)m, cudaMemcpyHostToDevice, s), "upload");
+        cuda_ok(cudaMemcpyAsync(d_bounds, bounds.data(), sizeof(int) * ((size_t)R + 1), cudaMemcpyHostToDevice, s), "bounds");
+        cuda_ok(cudaMemsetAsync(d_counts, 0, sizeof(int) * 3 * (size_t)R, s), "memset");
+        if (m > 0) kstep_route_count_kernel<<<(m + 255) / 256, 256, 0, s>>>(d_chunk, m, sim->bincnt, e->ts, R, d_bounds, d_dest, d_counts);
+        ++sim->launches;
+        cuda_ok(cudaMemcpyAsync(matrix.data() + (size_t)sim->rank * R, d_counts, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s), "counts");
+        cuda_ok(cudaStreamSynchronize(s), "sync");
+    }
+    // everybody learns the whole count matrix: matrix[src * R + dst]
+    if (st == PSIM_OK) st = comm_allreduce_ints(sim, matrix.data(), R * R, s);
+    long long n_recv = 0;
+    if (st == PSIM_OK) {
+        for (int r = 0; r < R; ++r) offs[(size_t)r + 1] = offs[(size_t)r] + matrix[(size_t)sim->rank * R + r];
+        for (int src = 0; src < R; ++src) n_recv += matrix[(size_t)src * R + sim->rank];
+        cuda_ok(cudaMemcpyAsync(d_counts + R, offs.data(), sizeof(int) * (size_t)R, cudaMemcpyHostToDevice, s), "offsets");
+        if (m > 0) kstep_route_pack_kernel<<<(m + 255) / 256, 256, 0, s>>>(d_chunk, m, lo, d_dest, d_counts + R, d_counts + 2 * R, d_rec, d_ids);
+        ++sim->launches;
+        cuda_ok(cudaGetLastError(), "route");
+    }
+    if (st == PSIM_OK) st = tmp.alloc(&d_recv, (size_t)std::max<long long>(n_recv, 1));
+    if (st == PSIM_OK) st = tmp.alloc(&d_recv_ids, (size_t)std::max<long long>(n_recv, 1));
+    if (st == PSIM_OK) st = comm_alltoall_records(sim, d_rec, d_ids, offs.data(), d_recv, d_recv_ids, matrix.data(), sizeof(double4), s);
+    if (st == PSIM_OK && n_recv > 0) {
+        kstep_fill_records_kernel<<<(unsigned)((n_recv + 255) / 256), 256, 0, s>>>(d_recv, d_recv_ids, (int)n_recv, sim->bincnt, e->ts, e->cap, e->ntx,
+                                                                                 e->tr_begin, e->tr_end, e->tr_begin - 1, e->pos[0], e->vel[0],
+                                                                                 e->sid[0], e->tcount, sim->d_err);
+        ++sim->launches;
+        cuda_ok(cudaGetLastError(), "fill");
+    }
+    if (st == PSIM_OK) cuda_ok(cudaStreamSynchronize(s), "sync");
+    tmp.release();
+    PSIM_TRY(st);
+    bool unsuitable = false;
+    return kstep_finish_fill(sim, &unsuitable);
+}
 
 // issue one launch (all owned rows) of nsub steps; slabs split it into a boundary and an interior launch
 static int kstep_issue(psim_sim* sim, KstepEngine* e, int nsub, bool store) {

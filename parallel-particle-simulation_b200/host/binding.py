@@ -176,6 +176,7 @@ class Simulation:
         L.psim_config_default(C.byref(cfg))
         cfg.engine, cfg.device, cfg.tile_cells, cfg.rank, cfg.nranks = engine, device, tile_cells, rank, nranks
         cfg.stream = stream
+        self._parts_ref = parts   # slabs upload cooperatively inside comm_connect: keep the caller's array alive until then
         self._h = C.c_void_p()
         _check(L.psim_create(C.byref(self._h), C.byref(cfg), _address(parts) if n else None, n, self.size), "psim_create")
 
@@ -247,6 +248,7 @@ class Simulation:
     def comm_connect(self, unique_id: bytes):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         _check(lib().psim_comm_connect(self._h, buf), "psim_comm_connect")
+        self._parts_ref = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
