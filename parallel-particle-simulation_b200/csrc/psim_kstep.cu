@@ -276,11 +276,19 @@ __device__ __forceinline__ void k_classify(KSmem<TS, H>& S, int p, int lr, int l
     S.pcode[p] = (unsigned short)oc;
 }
 
+// Walls (reference serial.cpp:53-61), out of line and through shared memory: only tiles whose region touches a wall get here,
+// and keeping the bounce loops out of pass 2 keeps their registers out of it too.
+static __device__ __noinline__ void k_reflect_in_place(double2* pos, double2* vel, double size) {
+    double2 q = *pos, v = *vel;
+    reflect_particle(q.x, q.y, v.x, v.y, size);
+    *pos = q;
+    *vel = v;
+}
+
 // One time step of the region in shared memory (everything between two __syncthreads of the kernel).
 
-// Returns (speed bound exceeded) << 31 | most pairs this warp listed.
 template <int TS, int H, bool kStoreAcc>
-static __device__ __forceinline__ unsigned kstep_substep(int s, int b, bool last, int rbase, int cbase, bool at_wall, int bincnt, double size,
+static __device__ __forceinline__ void kstep_substep(int s, int b, bool last, int rbase, int cbase, bool at_wall, int bincnt, double size,
                                                       int vlim_hi, double2* acc_tmp) {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
@@ -375,6 +383,12 @@ static __device__ __forceinline__ unsigned kstep_substep(int s, int b, bool last
         for (int ch = warp; ch < nch; ch += NW) {
             const int p = ch * 32 + lane;
             if (p < np) {
+                // (the buffer parity is laundered through an empty asm: the addresses derived from it are then recomputed per
+                // chunk -- two or three integer instructions each -- instead of being spilled to local memory across the loop)
+                int bl = b;
+                asm volatile("" : "+r"(bl));
+                const double2* posb = S.pos[bl];
+                double2* posn = S.pos[bl ^ 1];
                 const unsigned code = S.pcode[p], fc = code & 3u;
                 const double2 me = posb[p];
                 double2 v = S.vel[p];
@@ -400,21 +414,28 @@ static __device__ __forceinline__ unsigned kstep_substep(int s, int b, bool last
                 v.y = __dadd_rn(v.y, __dmul_rn(ay, kDt));
                 x = __dadd_rn(x, __dmul_rn(v.x, kDt));
                 y = __dadd_rn(y, __dmul_rn(v.y, kDt));
-                if (at_wall) reflect_particle(x, y, v.x, v.y, size);
                 too_fast |= max(__double2hiint(v.x) & 0x7FFFFFFF, __double2hiint(v.y) & 0x7FFFFFFF) >= vlim_hi;
                 posn[p] = make_double2(x, y);
                 S.vel[p] = v;
+                if (at_wall) {
+                    k_reflect_in_place(&posn[p], &S.vel[p], size);
+                    const double2 q = posn[p];
+                    x = q.x;
+                    y = q.y;
+                }
                 int lr, lc;
                 k_table_cell<TW>(x, y, rbase, cbase, at_wall, bincnt, lr, lc);
                 if (!last) {
-                    k_bin_particle<TS, H>(S, p, lr, lc, b ^ 1, (unsigned)(s + 2), S.u.t.bitmap[s + 1]);
+                    k_bin_particle<TS, H>(S, p, lr, lc, bl ^ 1, (unsigned)(s + 2), S.u.t.bitmap[s + 1]);
                 } else {
                     k_classify<TS, H>(S, p, lr, lc);
                     if (kStoreAcc) acc_tmp[p] = make_double2(ax, ay);
                 }
             }
         }
-        return (too_fast ? 0x80000000u : 0u) | (unsigned)min(wbase, 0xFFFF);
+        // diagnostics and the speed flag go straight to shared memory: nothing stays live across the sub-steps
+        if (__any_sync(0xffffffffu, too_fast) && lane == 0) atomicOr(&S.flags, kErrSpeedBound);
+        if (lane == 0 && wbase > S.hw_pairs) atomicMax(&S.hw_pairs, wbase);
     }
 }
 
@@ -433,7 +454,6 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
     if (*reinterpret_cast<volatile int*>(P.err + 8) != 0) return;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int nsub = P.nsub;
     const int vlim_hi = __double2hiint(P.vlim);   // speeds are compared by the high words of their absolute values
     const int G = gridDim.x;
@@ -446,9 +466,6 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
     }
     if (tid < 9) S.segcnt[tid] = 0;
     if (tid < 8) S.ringcnt[tid] = 0;
-    bool too_fast = false;
-    int hw_pairs = 0;
-
     // ---- loader (warp 0) ---------------------------------------------------------------------------------------------------
     // Slot range `lane` (< kRanges) of the region of launch tile t: length and first global slot.  The headers of a tile are
     // fetched one tile before its bulk copies are issued, the bulk copies one tile before the data is used.
@@ -469,12 +486,11 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
     };
     Walk cur{(int)blockIdx.x, P.lrow0 + ((int)blockIdx.x / P.ntx) * P.row_stride, (int)blockIdx.x % P.ntx};
     Walk fw = cur;   // the tile whose headers are fetched next
-    const int rt_dr = lane < kRanges ? kRangeTab[lane][0] : 0, rt_dc = lane < kRanges ? kRangeTab[lane][1] : 0;
-    const int rt_cb = lane < kRanges ? kRangeTab[lane][2] : 0, rt_ce = lane < kRanges ? kRangeTab[lane][3] : 0;
     auto fetch_range = [&](int& len, int& src) {
         len = 0;
         src = 0;
         if (fw.t < P.ntiles && lane < kRanges && (lane == 0 || nsub > 0)) {
+            const int rt_dr = kRangeTab[lane][0], rt_dc = kRangeTab[lane][1], rt_cb = kRangeTab[lane][2], rt_ce = kRangeTab[lane][3];
             const int ntr = P.tr_base + fw.lrow + rt_dr, ntc = fw.tc + rt_dc;
             if (ntr >= 0 && ntr < P.nty && ntc >= 0 && ntc < P.ntx) {
                 const int nlt = (fw.lrow + rt_dr) * P.ntx + ntc;
@@ -616,10 +632,8 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
 
         // ---- the fused time steps ----------------------------------------------------------------------------------
         for (int s = 0; s < nsub; ++s) {
-            const unsigned r = kstep_substep<TS, H, kStoreAcc>(s, (b0 + s) & 1, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size,
-                                                               vlim_hi, P.acc_tmp + (size_t)blockIdx.x * NMAX);
-            too_fast |= (r >> 31) != 0u;
-            hw_pairs = max(hw_pairs, (int)(r & 0xFFFFu));
+            kstep_substep<TS, H, kStoreAcc>(s, (b0 + s) & 1, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size, vlim_hi,
+                                            P.acc_tmp + (size_t)blockIdx.x * NMAX);
             if (s + 1 == nsub) k_fence_proxy_async();   // my accesses to the cell table and the free position buffer precede the next tile's bulk copies
             __syncthreads();
         }
@@ -713,9 +727,6 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
         __syncthreads();   // the tile is completely stored: velocities, codes and the final position buffer may be overwritten
     }
     // ---- report ------------------------------------------------------------------------------------------------------
-    if (__any_sync(0xffffffffu, too_fast) && lane == 0) atomicOr(&S.flags, kErrSpeedBound);
-    for (int o = 16; o > 0; o >>= 1) hw_pairs = max(hw_pairs, __shfl_xor_sync(0xffffffffu, hw_pairs, o));
-    if (lane == 0) atomicMax(&S.hw_pairs, hw_pairs);
     __syncthreads();
     if (tid == 0) {
         if (S.flags) {
