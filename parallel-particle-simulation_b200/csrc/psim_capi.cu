@@ -404,7 +404,6 @@ void psim_config_default(psim_config* cfg) {
     std::memset(cfg, 0, sizeof *cfg);
     cfg->engine = PSIM_ENGINE_AUTO;
     cfg->device = -1;
-    cfg->use_graph = -1;
     cfg->nranks = 1;
 }
 

@@ -1079,6 +1079,7 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     e->ksteps = e->kmax;
     if (const char* r = std::getenv("PSIM_RINGSORT")) e->ringsort = std::atoi(r) != 0;
     if (const char* k = std::getenv("PSIM_KSTEPS")) e->ksteps = std::min(std::max(std::atoi(k), 1), e->kmax);
+    if (cfg->steps_per_launch > 0) e->ksteps = std::min(cfg->steps_per_launch, e->kmax);
     e->ntx = tiled_tile_rows(sim->bincnt, ts);
     if (sim->nranks > e->ntx) return fail(PSIM_ERR_INVALID, "more slabs (%d) than tile rows (%d)", sim->nranks, e->ntx);
     tiled_slab_rows(e->ntx, sim->rank, sim->nranks, &e->tr_begin, &e->tr_end);

@@ -42,7 +42,7 @@ class PsimError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("engine", C.c_int), ("device", C.c_int), ("stream", C.c_void_p), ("tile_cells", C.c_int),
-                ("use_graph", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("reserved", C.c_int * 8)]
+                ("steps_per_launch", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("reserved", C.c_int * 8)]
 
 
 class Stats(C.Structure):
@@ -167,7 +167,8 @@ class Simulation:
     """One simulation handle (psim_create ... psim_destroy)."""
 
     def __init__(self, parts, num_parts: int | None = None, size: float | None = None, *, engine: int = ENGINE_AUTO,
-                 device: int = -1, stream: int | None = None, tile_cells: int = 0, rank: int = 0, nranks: int = 1):
+                 device: int = -1, stream: int | None = None, tile_cells: int = 0, rank: int = 0, nranks: int = 1,
+                 steps_per_launch: int = 0):
         L = lib()
         n = int(num_parts if num_parts is not None else len(parts))
         self.n = n
@@ -175,6 +176,7 @@ class Simulation:
         cfg = Config()
         L.psim_config_default(C.byref(cfg))
         cfg.engine, cfg.device, cfg.tile_cells, cfg.rank, cfg.nranks = engine, device, tile_cells, rank, nranks
+        cfg.steps_per_launch = steps_per_launch
         cfg.stream = stream
         self._parts_ref = parts   # slabs upload cooperatively inside comm_connect: keep the caller's array alive until then
         self._h = C.c_void_p()
