@@ -128,6 +128,37 @@ def run_reference_harness(n, seed, steps, warmup, threads=None):
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
+def run_oracle_port(n, seed, steps, warmup):
+    """Fallback when oracle/_ref is absent (a clean checkout on a box without /root/reference): the oracle's C restatement
+    of part1/serial.cpp (oracle/psim_oracle.c, built here by its Makefile), one thread, same particles."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    from psim_testlib import Oracle
+
+    import __graft_entry__ as g
+
+    pkg = g.load_package()
+    size = pkg.box_size(n)
+    parts = np.zeros((n, 6))
+    pkg.init_particles(n, seed, size, out=parts)   # host-side generator of libpsim (no GPU involved)
+    orc = Oracle()
+    t0 = time.perf_counter()
+    orc.step(parts, size, warmup)
+    t1 = time.perf_counter()
+    orc.step(parts, size, steps)
+    t2 = time.perf_counter()
+    return {"particle_steps_per_s": n * steps / (t2 - t1), "steps_s": t2 - t1, "init_s": t1 - t0, "threads": 1, "kind": "port"}
+
+
+def cpu_reference(n, seed, steps, warmup):
+    """(result dict, kind, description): the unmodified reference if its binaries travelled with the snapshot, else the port"""
+    if os.path.exists(REF_HARNESS):
+        r = run_reference_harness(n, seed, steps, warmup)
+        return r, "reference", "the unmodified part1/openmp.cpp"
+    r = run_oracle_port(n, seed, max(1, min(steps, 3)), 1)
+    return r, "port", "oracle/psim_oracle.c (C restatement of part1/serial.cpp; oracle/_ref was not built on this checkout)"
+
+
 def reference_arm(args):
     """The reference's own CPU implementation (unmodified part1/openmp.cpp) on this box's cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -137,16 +168,18 @@ def reference_arm(args):
     # bounded sample: ~1 s per 20 M-particle step on 16 cores -> cap the timed steps
     k = max(1, min(args.steps, 20))
     w = max(1, min(args.warmup, 3))
-    r = run_reference_harness(n, args.seed, k, w)
+    r, kind, what = cpu_reference(n, args.seed, k, w)
+    if kind == "port":
+        k, w = max(1, min(k, 3)), 1
     value = r["particle_steps_per_s"]
-    sample = f"{n} particles, seed {args.seed}, {w} warm-up + {k} timed steps of the unmodified part1/openmp.cpp"
+    sample = f"{n} particles, seed {args.seed}, {w} warm-up + {k} timed steps of {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
         "steps": k, "warmup": w, "ms_per_step": 1e3 * r["steps_s"] / k, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_string(n, args.seed), "baseline_config": baseline_config(n, args.gpus, args.scaling),
                    "particles": n, "requested_steps": args.steps, "init_simulation_s": r["init_s"]},
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": r["threads"], "kind": "reference",
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": r["threads"], "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -357,11 +390,11 @@ def main():
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_reference_harness(n, args.seed, args.cpu_sample_steps, 1)
+            r, kind, what = cpu_reference(n, args.seed, args.cpu_sample_steps, 1)
             line["cpu_baseline"] = {
-                "value": r["particle_steps_per_s"], "unit": "particle-steps/s", "cores": r["threads"], "kind": "reference",
-                "sample": f"{n} particles, seed {args.seed}, 1 warm-up + {args.cpu_sample_steps} timed steps of the unmodified "
-                          f"part1/openmp.cpp (init_simulation {r['init_s']:.1f} s not counted)"}
+                "value": r["particle_steps_per_s"], "unit": "particle-steps/s", "cores": r["threads"], "kind": kind,
+                "sample": f"{n} particles, seed {args.seed}, 1 warm-up + {args.cpu_sample_steps if kind == 'reference' else min(args.cpu_sample_steps, 3)} "
+                          f"timed steps of {what} (init / warm-up {r['init_s']:.1f} s not counted)"}
         except Exception as exc:  # the bench line must still appear
             line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {exc}"}
