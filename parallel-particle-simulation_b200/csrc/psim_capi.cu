@@ -100,13 +100,15 @@ __global__ void __launch_bounds__(kObsThreads) members_rank_kernel(SoAView v, in
 // sorted copies of the positions for the statistics pass
 __global__ void __launch_bounds__(kObsThreads) sort_xy_kernel(SoAView v, int bincnt, const int* __restrict__ cell_start,
                                                               const int* __restrict__ slot, double* __restrict__ sx,
-                                                              double* __restrict__ sy) {
+                                                              double* __restrict__ sy, unsigned char* __restrict__ owned_sorted,
+                                                              int n_owned) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
     const int c = axis_cell(v.x[i], bincnt) * bincnt + axis_cell(v.y[i], bincnt);
     const int d = cell_start[c] + slot[i];
     sx[d] = v.x[i];
     sy[d] = v.y[i];
+    if (owned_sorted) owned_sorted[d] = i < n_owned;   // entries past n_owned are ghost particles: neighbours only
 }
 
 // order-independent fingerprint of the owned particles: sum over particles of a 64-bit mix of (id, x, y, vx, vy) bits
@@ -178,11 +180,12 @@ struct StatsPartial {
 
 __global__ void __launch_bounds__(kObsThreads) stats_kernel(const double* __restrict__ sx, const double* __restrict__ sy, int n,
                                                             SoAView v, int bincnt, const int* __restrict__ cell_start,
+                                                            const unsigned char* __restrict__ owned_sorted, int n_owned,
                                                             StatsPartial* __restrict__ partial) {
     __shared__ StatsPartial s_part[kObsThreads / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     StatsPartial p{1.0, 0.0, 0.0, 0.0, 0, 0, 0, 0};
-    if (i < n) {
+    if (i < n && (!owned_sorted || owned_sorted[i])) {
         const double xi = sx[i], yi = sy[i];
         const int row = axis_cell(xi, bincnt), col = axis_cell(yi, bincnt);
         const int c_lo = max(col - 1, 0), c_hi = min(col + 1, bincnt - 1);
@@ -207,6 +210,8 @@ __global__ void __launch_bounds__(kObsThreads) stats_kernel(const double* __rest
         p.maxnb = nb;
         const long long c = (long long)row * bincnt + col;
         p.maxcell = cell_start[c + 1] - cell_start[c];
+    }
+    if (i < n_owned) {
         const double vx = v.vx[i], vy = v.vy[i];  // any order: kinetic terms are per particle
         const double v2 = vx * vx + vy * vy;
         p.ke = 0.5 * kMass * v2;
@@ -889,20 +894,46 @@ int psim_stats(psim_sim* sim, psim_stats_t* out) {
     std::memset(out, 0, sizeof *out);
     out->dmin = 1.0;
     if (v.n == 0) return PSIM_OK;
-    const int blocks = (v.n + kObsThreads - 1) / kObsThreads;
     CellBinner b;
     DeviceArena tmp;
     double *sx = nullptr, *sy = nullptr;
     StatsPartial* part = nullptr;
-    int st = b.init(sim->bincnt, v.n);
-    if (st == PSIM_OK) st = b.build(v.x, v.y, v.n, s);
-    if (st == PSIM_OK) st = tmp.alloc(&sx, (size_t)v.n);
-    if (st == PSIM_OK) st = tmp.alloc(&sy, (size_t)v.n);
+    int st = PSIM_OK;
+    // A slab of the kstep engine also looks at the particles in its ghost rows (the neighbours' boundary bands), as
+    // neighbours only: pairs that straddle a slab border are then counted on both sides, like inside one slab, and the
+    // per-slab numbers of all ranks add up to the single-GPU numbers.
+    const int n_owned = v.n;
+    SoAView all = v;
+    unsigned char* owned_sorted = nullptr;
+    if (sim->engine == PSIM_ENGINE_KSTEP && sim->nranks > 1) {
+        const int ghost_cap = kstep_ghost_capacity(sim);
+        double *cx = nullptr, *cy = nullptr;
+        int n_ghost = 0;
+        st = tmp.alloc(&cx, (size_t)n_owned + ghost_cap);
+        if (st == PSIM_OK) st = tmp.alloc(&cy, (size_t)n_owned + ghost_cap);
+        if (st == PSIM_OK) st = tmp.alloc(&owned_sorted, (size_t)n_owned + ghost_cap);
+        if (st == PSIM_OK && (cudaMemcpyAsync(cx, v.x, sizeof(double) * (size_t)n_owned, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+                              cudaMemcpyAsync(cy, v.y, sizeof(double) * (size_t)n_owned, cudaMemcpyDeviceToDevice, s) != cudaSuccess))
+            st = fail(PSIM_ERR_CUDA, "psim_stats: %s", cudaGetErrorString(cudaGetLastError()));
+        if (st == PSIM_OK) st = kstep_ghost_positions(sim, cx + n_owned, cy + n_owned, ghost_cap, &n_ghost);
+        if (st != PSIM_OK) {
+            tmp.release();
+            return st;
+        }
+        all.x = cx;
+        all.y = cy;
+        all.n = n_owned + n_ghost;
+    }
+    const int blocks = (all.n + kObsThreads - 1) / kObsThreads;
+    if (st == PSIM_OK) st = b.init(sim->bincnt, all.n);
+    if (st == PSIM_OK) st = b.build(all.x, all.y, all.n, s);
+    if (st == PSIM_OK) st = tmp.alloc(&sx, (size_t)all.n);
+    if (st == PSIM_OK) st = tmp.alloc(&sy, (size_t)all.n);
     if (st == PSIM_OK) st = tmp.alloc(&part, (size_t)blocks);
     std::vector<StatsPartial> h((size_t)blocks);
     if (st == PSIM_OK) {
-        sort_xy_kernel<<<blocks, kObsThreads, 0, s>>>(v, sim->bincnt, b.cell_start, b.slot, sx, sy);
-        stats_kernel<<<blocks, kObsThreads, 0, s>>>(sx, sy, v.n, v, sim->bincnt, b.cell_start, part);
+        sort_xy_kernel<<<blocks, kObsThreads, 0, s>>>(all, sim->bincnt, b.cell_start, b.slot, sx, sy, owned_sorted, n_owned);
+        stats_kernel<<<blocks, kObsThreads, 0, s>>>(sx, sy, all.n, v, sim->bincnt, b.cell_start, owned_sorted, n_owned, part);
         sim->launches += 2;
         cudaError_t e = cudaMemcpyAsync(h.data(), part, sizeof(StatsPartial) * (size_t)blocks, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);

@@ -217,6 +217,8 @@ int kstep_exchange(psim_sim* sim, int parity, cudaStream_t s);  // psim_comm.cpp
 void kstep_shared_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, int* ntx);
 void kstep_row_ranges(psim_sim* sim, int parity, int lrow, char* ptr[4], size_t bytes[4]);
 int kstep_owned_rows(psim_sim* sim);
+int kstep_ghost_capacity(psim_sim* sim);
+int kstep_ghost_positions(psim_sim* sim, double* gx, double* gy, int capacity, int* count);   // neighbours for slab statistics
 bool kstep_fill_pending(psim_sim* sim);      // cooperative upload deferred to psim_comm_connect
 int kstep_distributed_fill(psim_sim* sim);
 int comm_allreduce_ints(psim_sim* sim, int* host_values, int count, cudaStream_t s);   // in place, sum

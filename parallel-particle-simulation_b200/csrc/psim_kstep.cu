@@ -1416,6 +1416,57 @@ int kstep_writeback(psim_sim* sim, particle_t* d_out, double2* d_xy) {
     return PSIM_OK;
 }
 
+// positions of the particles in the ghost rows' facing bands (the neighbours' boundary bands): neighbours for statistics
+__global__ void __launch_bounds__(128) kstep_ghost_gather_kernel(const double2* __restrict__ pos, const int* __restrict__ hdr, int cap, int ntx,
+                                                                 int row_lo, int row_hi, bool have_lo, bool have_hi, double* __restrict__ gx,
+                                                                 double* __restrict__ gy, int capacity, int* __restrict__ cursor) {
+    __shared__ int s_base;
+    const bool hi = blockIdx.x >= (unsigned)ntx;
+    if (hi ? !have_hi : !have_lo) return;
+    const int lt = (hi ? row_hi : row_lo) * ntx + (int)(blockIdx.x % ntx);
+    // lower ghost row = the lower neighbour's LAST row: its bottom band BR B BL (classes 4..6); upper ghost row: TL T TR (0..2)
+    const int* h = hdr + (size_t)lt * kHdrInts;
+    const int s0 = min(h[hi ? 0 : 4], cap), s1 = min(h[hi ? 3 : 7], cap), n = max(s1 - s0, 0);
+    if (threadIdx.x == 0) s_base = n ? atomicAdd(cursor, n) : 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (s_base + i >= capacity) break;
+        const double2 p = pos[(size_t)lt * cap + s0 + i];
+        gx[s_base + i] = p.x;
+        gy[s_base + i] = p.y;
+    }
+}
+
+int kstep_ghost_capacity(psim_sim* sim) { return 2 * sim->kstep->ntx * sim->kstep->cap; }
+
+int kstep_ghost_positions(psim_sim* sim, double* gx, double* gy, int capacity, int* count) {
+    KstepEngine* e = sim->kstep;
+    cudaStream_t s = sim->stream;
+    *count = 0;
+    if (sim->nranks == 1) return PSIM_OK;
+    if (!e->ghost_fresh) {
+        PSIM_TRY(kstep_exchange(sim, e->parity, s));
+        e->ghost_fresh = true;
+    }
+    if (sim->p2p) PSIM_TRY(comm_p2p_wait(sim, s));   // the neighbours' stores into my ghost rows are complete
+    int* d_cursor = nullptr;
+    PSIM_CUDA(cudaMalloc(&d_cursor, sizeof(int)));
+    cudaError_t err = cudaMemsetAsync(d_cursor, 0, sizeof(int), s);
+    const int p = e->parity;
+    if (err == cudaSuccess) {
+        kstep_ghost_gather_kernel<<<2 * e->ntx, 128, 0, s>>>(e->pos[p], e->hdr[p], e->cap, e->ntx, 0, e->lrows + 1, sim->rank > 0,
+                                                             sim->rank < sim->nranks - 1, gx, gy, capacity, d_cursor);
+        ++sim->launches;
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(count, d_cursor, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    cudaFree(d_cursor);
+    if (err != cudaSuccess) return fail(PSIM_ERR_CUDA, "kstep_ghost_positions: %s", cudaGetErrorString(err));
+    *count = std::min(*count, capacity);
+    return PSIM_OK;
+}
+
 void kstep_destroy(psim_sim* sim) {
     KstepEngine* e = sim->kstep;
     if (!e) return;

@@ -53,6 +53,12 @@ def main():
     dist.reduce(c, 0)
     info = sim.info()
     st = sim.stats()
+    sums = torch.tensor([st["pairs"], st["touched"]], dtype=torch.int64, device="cuda")
+    ke = torch.tensor([st["kinetic_energy"]], dtype=torch.float64, device="cuda")
+    dmin = torch.tensor([st["dmin"]], dtype=torch.float64, device="cuda")
+    dist.reduce(sums, 0)
+    dist.reduce(ke, 0)
+    dist.reduce(dmin, 0, op=dist.ReduceOp.MIN)
     sim.close()
     ok = True
     if rank == 0:
@@ -62,9 +68,15 @@ def main():
         counts = c.cpu().numpy()
         once = bool((counts == 1).all())
         same = bool(np.array_equal(got, want))
-        ok = once and same
+        # per-slab statistics count the pairs that straddle a slab border on both sides (ghost rows are neighbours): the sums
+        # over the slabs must equal the oracle's numbers for the whole box
+        ost = orc.stats(want, size)
+        stats_ok = (engine_name != "kstep") or (int(sums[0]) == ost["pairs"] and int(sums[1]) == ost["touched"]
+                                                 and abs(float(dmin[0]) - ost["dmin"]) <= 1e-15
+                                                 and abs(float(ke[0]) - ost["ke"]) <= 1e-9 * ost["ke"])
+        ok = once and same and stats_ok
         print(f"SLAB_CHECK {'ok' if ok else 'FAIL'} engine={engine_name} ranks={world} n={n} steps={done} tile={tile} owned_once={once} "
-              f"bit_identical={same} max_abs_diff={np.abs(got - want).max():.3e} rows={info['row_begin']}..{info['row_end']}", flush=True)
+              f"bit_identical={same} stats_equal_oracle={stats_ok} max_abs_diff={np.abs(got - want).max():.3e} rows={info['row_begin']}..{info['row_end']}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
