@@ -66,8 +66,12 @@ namespace psim {
 template <int TS, int H> struct KCfg;
 template <> struct KCfg<16, 3> { static constexpr int KMAX = 2, T = 64,  CTAS = 8, CAP = 128,  NMAX = 256; };
 template <> struct KCfg<16, 4> { static constexpr int KMAX = 3, T = 64,  CTAS = 8, CAP = 128,  NMAX = 288; };
-template <> struct KCfg<32, 3> { static constexpr int KMAX = 2, T = 128, CTAS = 5, CAP = 352,  NMAX = 480; };
-template <> struct KCfg<32, 4> { static constexpr int KMAX = 3, T = 128, CTAS = 5, CAP = 352,  NMAX = 512; };
+#ifndef PSIM_KSTEP_T32
+#define PSIM_KSTEP_T32 128
+#define PSIM_KSTEP_C32 5
+#endif
+template <> struct KCfg<32, 3> { static constexpr int KMAX = 2, T = PSIM_KSTEP_T32, CTAS = PSIM_KSTEP_C32, CAP = 352,  NMAX = 480; };
+template <> struct KCfg<32, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T32, CTAS = PSIM_KSTEP_C32, CAP = 352,  NMAX = 512; };
 #ifndef PSIM_KSTEP_T64
 #define PSIM_KSTEP_T64 384
 #endif

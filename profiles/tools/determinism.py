@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Race hunt without a sanitizer: the same simulation under different schedules (CTAs per SM, tile size, engine) must
-end in bit-identical states (the summation order is canonical, so any difference is a race or a lost update)."""
+end in bit-identical states -- the kstep engine for every tile size / halo width / number of fused steps, with and without the
+ring culling, against the tiled and cellsort engines (the summation order is canonical, so any difference is a race or a lost update)."""
 import hashlib, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -10,13 +11,18 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     pkg = g.load_package()
     n, steps, tile, engine = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
     parts = pkg.init_particles(n, 42)
-    sim = pkg.Simulation(parts, n, pkg.box_size(n), engine=pkg.ENGINE_TILED if engine == "tiled" else pkg.ENGINE_CELLSORT, tile_cells=tile)
+    eng = {"tiled": pkg.ENGINE_TILED, "kstep": pkg.ENGINE_KSTEP, "cellsort": pkg.ENGINE_CELLSORT}[engine]
+    sim = pkg.Simulation(parts, n, pkg.box_size(n), engine=eng, tile_cells=tile)
     out = sim.step(steps).sync().read_particles()
     print("HASH", hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest(), sim.info()["reserved_hw_pairs"])
     sys.exit(0)
 n, steps = int(sys.argv[1]), int(sys.argv[2])
 hashes = {}
-for name, env, tile, engine in [("t32 4cta", {}, 32, "tiled"), ("t32 4cta again", {}, 32, "tiled"), ("t32 1cta", {"PSIM_CTAS_PER_SM": "1"}, 32, "tiled"),
+for name, env, tile, engine in [("kstep64 K3 H4", {}, 64, "kstep"), ("kstep64 again", {}, 64, "kstep"), ("kstep64 1cta", {"PSIM_CTAS_PER_SM": "1"}, 64, "kstep"),
+                                ("kstep64 K2", {"PSIM_KSTEPS": "2"}, 64, "kstep"), ("kstep64 K1", {"PSIM_KSTEPS": "1"}, 64, "kstep"),
+                                ("kstep64 H3 K2", {"PSIM_HALO": "3"}, 64, "kstep"), ("kstep64 noring", {"PSIM_RINGSORT": "0"}, 64, "kstep"),
+                                ("kstep32", {}, 32, "kstep"), ("kstep16", {}, 16, "kstep"),
+                                ("t32 4cta", {}, 32, "tiled"), ("t32 4cta again", {}, 32, "tiled"), ("t32 1cta", {"PSIM_CTAS_PER_SM": "1"}, 32, "tiled"),
                                 ("t32 3cta", {"PSIM_CTAS_PER_SM": "3"}, 32, "tiled"), ("t16", {}, 16, "tiled"), ("t64", {}, 64, "tiled"),
                                 ("cellsort", {}, 0, "cellsort")]:
     r = subprocess.run([sys.executable, __file__, "child", str(n), str(steps), str(tile), engine], capture_output=True, text=True,
