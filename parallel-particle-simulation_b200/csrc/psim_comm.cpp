@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -432,7 +433,14 @@ extern "C" int psim_comm_connect(psim_sim* sim, const unsigned char id128[128]) 
     PSIM_CUDA(cudaStreamCreateWithPriority(&sim->comm_stream, cudaStreamNonBlocking, hi));   // exchange first
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_boundary, cudaEventDisableTiming));
     PSIM_CUDA(cudaEventCreateWithFlags(&sim->ev_exchanged, cudaEventDisableTiming));
+    static const bool trace = std::getenv("PSIM_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if (kstep_fill_pending(sim)) PSIM_TRY(kstep_distributed_fill(sim));   // cooperative upload: needs the communicator
+    const double t1 = now();
     if (sim->tiled || sim->kstep) PSIM_TRY(p2p_setup(sim, comm));
+    if (trace)
+        std::fprintf(stderr, "[psim trace] connect rank %d: cooperative fill %.3f ms, peer-memory setup %.3f ms\n", sim->rank, 1e3 * (t1 - t0),
+                     1e3 * (now() - t1));
     return PSIM_OK;
 }

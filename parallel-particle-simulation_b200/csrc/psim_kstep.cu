@@ -1191,6 +1191,16 @@ int kstep_distributed_fill(psim_sim* sim) {
     const particle_t* parts = e->pending_parts;
     e->pending_parts = nullptr;
     const int lo = (int)((long long)n * sim->rank / R), hi = (int)((long long)n * (sim->rank + 1) / R), m = hi - lo;
+    static const bool trace = std::getenv("PSIM_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        const double t = now();
+        std::fprintf(stderr, "[psim trace] distributed fill rank %d: %-24s %8.3f ms\n", sim->rank, what, 1e3 * (t - t_prev));
+        t_prev = t;
+    };
     DeviceArena tmp;
     particle_t* d_chunk = nullptr;
     double4 *d_rec = nullptr, *d_recv = nullptr;
@@ -1222,8 +1232,10 @@ int kstep_distributed_fill(psim_sim* sim) {
         cuda_ok(cudaMemcpyAsync(matrix.data() + (size_t)sim->rank * R, d_counts, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s), "counts");
         cuda_ok(cudaStreamSynchronize(s), "sync");
     }
+    lap("alloc + upload + route");
     // everybody learns the whole count matrix: matrix[src * R + dst]
     if (st == PSIM_OK) st = comm_allreduce_ints(sim, matrix.data(), R * R, s);
+    lap("allreduce counts");
     long long n_recv = 0;
     if (st == PSIM_OK) {
         for (int r = 0; r < R; ++r) offs[(size_t)r + 1] = offs[(size_t)r] + matrix[(size_t)sim->rank * R + r];
@@ -1235,7 +1247,9 @@ int kstep_distributed_fill(psim_sim* sim) {
     }
     if (st == PSIM_OK) st = tmp.alloc(&d_recv, (size_t)std::max<long long>(n_recv, 1));
     if (st == PSIM_OK) st = tmp.alloc(&d_recv_ids, (size_t)std::max<long long>(n_recv, 1));
+    lap("pack + alloc recv");
     if (st == PSIM_OK) st = comm_alltoall_records(sim, d_rec, d_ids, offs.data(), d_recv, d_recv_ids, matrix.data(), sizeof(double4), s);
+    lap("all-to-all");
     if (st == PSIM_OK && n_recv > 0) {
         kstep_fill_records_kernel<<<(unsigned)((n_recv + 255) / 256), 256, 0, s>>>(d_recv, d_recv_ids, (int)n_recv, sim->bincnt, e->ts, e->cap, e->ntx,
                                                                                  e->tr_begin, e->tr_end, e->tr_begin - 1, e->pos[0], e->vel[0],
@@ -1244,10 +1258,14 @@ int kstep_distributed_fill(psim_sim* sim) {
         cuda_ok(cudaGetLastError(), "fill");
     }
     if (st == PSIM_OK) cuda_ok(cudaStreamSynchronize(s), "sync");
+    lap("fill stripes");
     tmp.release();
+    lap("free staging");
     PSIM_TRY(st);
     bool unsuitable = false;
-    return kstep_finish_fill(sim, &unsuitable);
+    st = kstep_finish_fill(sim, &unsuitable);
+    lap("check + partition");
+    return st;
 }
 
 // issue one launch (all owned rows) of nsub steps; slabs split it into a boundary and an interior launch
