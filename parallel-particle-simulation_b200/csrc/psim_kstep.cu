@@ -20,7 +20,10 @@
 // H >= K * (1 + d / cutoff) the tile itself lies in U_K.  d is enforced, not assumed: every computed velocity
 // component is compared with d / dt in every sub-step (all loaded particles, so that no mis-computed halo particle
 // can jump into the trusted region either); a violation raises kErrSpeedBound, later launches become no-ops, and the
-// host replays the batch from the untouched input buffers with K = 1 (d = H - 1 cells; kstep_recover).
+// host replays the batch from the untouched input buffers with K = 1 (d = H - 1 cells; kstep_after_sync) or, beyond that
+// and for capacity overflows, hands the state over to the cellsort engine (psim_capi.cu: switch_to_cellsort).
+// Ring culling: a halo particle r cells away from the tile matters only through sub-step H - 1 - r; the halo is sorted by
+// ring on arrival and the passes of sub-step s stop at nproc[s].
 //
 // Layout in HBM.  Tiles of TS x TS cutoff cells; a tile owns a stripe of CAP slots in three streams pos (double2),
 // vel (double2), id (int), double buffered by launch parity, plus acc (double2) for launches that keep the last
@@ -30,8 +33,12 @@
 // ranges (own stripe, four edge bands -- the E neighbour's left band wraps around the ring and takes two -- and four
 // corners), each one TMA bulk copy (cp.async.bulk -> UBLKCP) for pos and one for vel, completion on an mbarrier.
 //
-// The kernel (kstep_kernel<TS, acc, peer>): persistent CTAs, one tile at a time, T threads:
-//   load     10 ranges -> shared memory (TMA for pos / vel, plain loads for the ids); wipe the cell table
+// The kernel (kstep_kernel<TS, H, acc, peer>): persistent CTAs, one tile at a time, T threads:
+//   load     (one tile ahead, by the last warp) headers of the next tile are fetched while the current one computes; its 10
+//            ranges are bulk-copied the moment the current tile's last search is over -- positions into the position buffer
+//            that tile no longer needs, velocities into a landing zone that aliases the (then dead) cell table -- so the
+//            copies fly during the store phase, from which the loader warp is excused (named barrier of the other warps)
+//   arrive   velocities leave the landing zone, the halo is ring-sorted, own ids are parked, the cell table is wiped
 //   bin      every loaded particle into a (TS+2H+2)^2 cell table in shared memory: per cell the head of a linked list
 //            (reference part3/gpu.cu:92-112 does this in global memory with 16 fixed slots) + one occupancy bit
 //   K times  pass 1  each particle takes the 9 occupancy bits of its 3x3 neighbourhood (reference serial.cpp:102-117),
