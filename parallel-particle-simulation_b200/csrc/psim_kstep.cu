@@ -87,47 +87,55 @@ template <> struct KCfg<64, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T
 
 constexpr int kHdrInts = 16;          // per tile: ten prefix offsets (ring order TL T TR R BR B BL L M, [9] = population)
 constexpr int kRanges = 10;           // slot ranges that make up a tile's region
-constexpr unsigned kIdxBits = 11;     // list entries: sub-step number << 11 | particle slot in shared memory
-constexpr unsigned kIdxMask = (1u << kIdxBits) - 1u;
 constexpr unsigned kNoOwner = 0xFFFFu;
+constexpr int kGuard = 2;             // empty guard rings around the cell table: the candidate search looks two cells out
+constexpr int kSlowMax = 16;          // in-range neighbours the canonical-order path sorts (beyond: hand-over to cellsort)
+// per-particle force word: count << 28 | second reference << 14 | first reference; a reference is the slot of an
+// evaluated pair (13 bits) plus one bit that says "I am the pair's second particle: negate"
+constexpr unsigned kRefBits = 14, kRefMask = (1u << kRefBits) - 1u, kRefNeg = 1u << 13, kCntShift = 28;
 
 template <int TS, int H> struct KDims {
     using C = KCfg<TS, H>;
-    static constexpr int TW = TS + 2 * H + 2;                  // cell table side: tile + halo + one guard ring (never occupied)
-    static constexpr int NC = TW * TW, NC4 = (NC + 3) / 4 * 4;
+    static constexpr int TW = TS + 2 * H + 2 * kGuard;         // cell table side: tile + halo + guard rings (never occupied)
+    static constexpr int NC = TW * TW, NC8 = (NC + 7) / 8 * 8;
     static constexpr int RW = (TW + 31) / 32 + 1;              // occupancy words per table row (+1: funnel shifts read one past)
-    static constexpr int BM = (TW * RW + 3) / 4 * 4;           // one occupancy map, padded to 16 bytes
+    static constexpr int BM = (TW * RW + 3) / 4 * 4;           // the occupancy map, padded to 16 bytes
     static constexpr int NW = C::T / 32;
-    static_assert(TS >= 2 * H && C::KMAX < H && C::NMAX <= (int)kIdxMask && C::T % 32 == 0 && C::CAP <= 0xFFF, "configuration");
+    static constexpr int PCAP = 2 * C::NMAX;                   // candidate pairs of one region (expected 1.25 per particle)
+    static constexpr int NCON = C::NMAX / 2;                   // in-range pairs of one sub-step (expected 0.1 per particle)
+    static_assert(TS >= 2 * H && C::KMAX < H && C::NMAX < 0xFFF && C::T % 32 == 0 && C::CAP <= 0xFFF, "configuration");
     static_assert(TW <= 255, "cell codes pack row and column into 8 bits each");
+    static_assert(NCON < (int)kRefNeg, "pair references are 13 bits");
 };
 
 template <int TS, int H> struct __align__(16) KSmem {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
-    struct Tables {
-        alignas(16) unsigned head[D::NC4];             // per cell: list heads, low half = even position buffer, high half = odd
-        alignas(16) unsigned bitmap[C::KMAX][D::BM];   // per sub-step: one occupancy bit per cell
+    struct Tables {   // everything the candidate search needs; dead once the last sub-step has evaluated its pairs
+        alignas(16) unsigned short head[D::NC8];   // per cell: first particle of its list (slot + 1, 0 = empty)
+        alignas(16) unsigned bitmap[D::BM];        // one occupancy bit per cell
+        alignas(16) unsigned short next[C::NMAX];  // list links (slot + 1, 0 = end)
+        alignas(16) unsigned pairs[D::PCAP];       // candidate pairs i | j << 16: every pair that can come within the cutoff during this launch
     };
     double2 pos[2][C::NMAX];                 // positions, double buffered by sub-step (TMA destination: the buffer the previous tile left free)
     double2 vel[C::NMAX];                    // velocities (only the owner lane of a particle touches them during the sub-steps)
-    double2 wres[D::NW][32];                 // per warp: contribution of listed pair e to its first particle
+    double2 wres[D::NCON];                   // contribution of evaluated pair g to its first particle (the second one takes the negative)
     union alignas(16) {
         Tables t;
         double2 vland[C::NMAX];              // landing zone of the NEXT tile's velocities while this tile is stored (TMA destination)
     } u;
-    unsigned wij[D::NW][32];                 // per warp: listed pairs, i | j << 16
-    unsigned short next[2][C::NMAX];         // list links, double buffered like the heads
-    unsigned short ccode[C::NMAX];           // table row << 8 | table column of a particle's current cell
-    unsigned short pcode[C::NMAX];           // pass 1 -> pass 2: pair count | list base << 2;  store phase: class << 12 | rank
+    unsigned pw[C::NMAX];                    // bin -> search: table row << 8 | column;  sub-steps: force word;  store phase: class << 12 | rank
+    unsigned wlist[D::NW][32];               // per warp: in-range pairs waiting for their dense evaluation
+    unsigned short wslow[D::NW][kSlowMax];   // per warp: neighbours of a particle on the canonical-order path (rank << 12 | slot)
     int id[C::CAP];                          // ids of the tile's own stripe (halo particles that end up inside fetch theirs at store time)
-    unsigned short horig[C::T];          // halo particle -> its shared slot before the ring sort (id look-up at store time)
+    unsigned short horig[C::T];              // halo particle -> its shared slot before the ring sort (id look-up at store time)
     unsigned long long mbar;                 // TMA completion
     int rsrc[2][kRanges], rlen[2][kRanges], rdst[2][kRanges];   // slot ranges of this tile / the next: global slot, length, first shared slot
     int ncount[2];                           // particles of this tile's / the next tile's region
     int nproc[8];                            // per sub-step: particles that are still processed (own + rings that still matter)
     int ringcnt[8];
     int segcnt[12], segoff[12];
+    int npairs, ncon, work;
     int flags, hw_region, hw_stripe, hw_pairs;
 };
 
@@ -160,7 +168,8 @@ struct KParams {
     int bincnt;
     double size;
     int nsub;             // steps fused in this launch (0: only re-partition the stripes)
-    double vlim;          // |v| component bound that keeps the halo argument valid for nsub steps: d / dt
+    double vlim2;         // square of the speed bound that keeps the halo argument and the candidate list valid for nsub steps
+    double rs2;           // square of the candidate radius: cutoff + twice the distance the speed bound allows in nsub - 1 steps
     int* err;
     int seq;              // launch number (reported with the first error)
     int ringsort;         // order the halo by ring and stop processing rings that no longer matter
@@ -198,35 +207,14 @@ __device__ __forceinline__ void k_tma_load_1d(void* dst_smem, const void* src_gm
                  "l"(src_gmem), "r"(bytes), "r"(k_smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void k_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Rare path: exact walk of the 3x3 neighbourhood with canonical-order summation (particles with three or more
-// in-range neighbours, or whose pairs did not fit the warp's list).
-template <int TS, int H>
-static __device__ __noinline__ double2 kslow_force(const KSmem<TS, H>& S, int b, unsigned vb, int i, int cell) {
-    constexpr int TW = KDims<TS, H>::TW;
-    const double2* xy = S.pos[b];
-    const unsigned short* next = S.next[b];
-    const double2 pi = xy[i];
-    auto visit = [&](auto&& f) {
-#pragma unroll 1
-        for (int k = 0; k < 9; ++k) {
-            const unsigned w = S.u.t.head[cell + (k / 3 - 1) * TW + (k % 3 - 1)];
-            unsigned h = b ? w >> 16 : w & 0xFFFFu;
-            while (h >= vb) {
-                const unsigned j = h & kIdxMask;
-                const double2 pj = xy[j];
-                f(pj.x, pj.y, k);
-                h = next[j];
-            }
-        }
-    };
-    auto rank_of = [&](double, double, int k) { return visit_rank(k / 3 - 1, k % 3 - 1); };
-    double ax, ay;
-    int nb;
-    accumulate_force(pi.x, pi.y, visit, rank_of, ax, ay, nb);
-    return make_double2(ax, ay);
+// one hardware shared-memory atomic per lane (the compiler would otherwise wrap atomicAdd into a ballot / leader / shuffle
+// sequence of a dozen instructions; the few lanes of a diverged warp that get here are cheaper served by the LSU)
+__device__ __forceinline__ int k_atoms_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(k_smem_u32(p)), "r"(v) : "memory");
+    return old;
 }
+__device__ __forceinline__ void k_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // the K-step kernel
@@ -241,30 +229,31 @@ __device__ __forceinline__ void k_table_cell(double x, double y, int rbase, int 
         gr = min(max(gr, 0), bincnt - 1);
         gc = min(max(gc, 0), bincnt - 1);
     }
-    lr = min(max(gr - rbase, 1), TW - 2);
-    lc = min(max(gc - cbase, 1), TW - 2);
+    lr = min(max(gr - rbase, kGuard), TW - 1 - kGuard);
+    lc = min(max(gc - cbase, kGuard), TW - 1 - kGuard);
 }
-// insert particle p into the list of its cell (table parity tb, entries tagged with sub-step number ver)
+// insert particle p into the list of its cell (two 16-bit heads share a word: exchange one half, keep the other)
 template <int TS, int H>
-__device__ __forceinline__ void k_bin_particle(KSmem<TS, H>& S, int p, int lr, int lc, int tb, unsigned ver, unsigned* bm) {
+__device__ __forceinline__ void k_bin_particle(KSmem<TS, H>& S, int p, int lr, int lc) {
     constexpr int TW = KDims<TS, H>::TW, RW = KDims<TS, H>::RW;
-    unsigned* w = &S.u.t.head[lr * TW + lc];
-    const unsigned ent = (ver << kIdxBits) | (unsigned)p;
+    const int cell = lr * TW + lc;
+    unsigned* w = reinterpret_cast<unsigned*>(S.u.t.head) + (cell >> 1);
+    const unsigned sh = (unsigned)(cell & 1) << 4;
+    const unsigned ent = (unsigned)(p + 1) << sh, keep = ~(0xFFFFu << sh);
     unsigned old = *w;
-    for (;;) {   // exchange one half of the word, keep the other (it belongs to the table that is being searched)
-        const unsigned nw = tb ? ((old & 0xFFFFu) | (ent << 16)) : ((old & 0xFFFF0000u) | ent);
-        const unsigned prev = atomicCAS(w, old, nw);
+    for (;;) {
+        const unsigned prev = atomicCAS(w, old, (old & keep) | ent);
         if (prev == old) break;
         old = prev;
     }
-    S.next[tb][p] = (unsigned short)(tb ? old >> 16 : old & 0xFFFFu);   // an older sub-step's entry ends the list
-    S.ccode[p] = (unsigned short)((lr << 8) | lc);
-    atomicOr(&bm[lr * RW + (lc >> 5)], 1u << (lc & 31));
+    S.u.t.next[p] = (unsigned short)((old >> sh) & 0xFFFFu);
+    S.pw[p] = (unsigned)((lr << 8) | lc);
+    atomicOr(&S.u.t.bitmap[lr * RW + (lc >> 5)], 1u << (lc & 31));
 }
 // final cell -> owner test, class, rank inside the class
 template <int TS, int H>
 __device__ __forceinline__ void k_classify(KSmem<TS, H>& S, int p, int lr, int lc) {
-    const int er = lr - (H + 1), ec = lc - (H + 1);
+    const int er = lr - (H + kGuard), ec = lc - (H + kGuard);
     unsigned oc = kNoOwner;
     const bool mine = (unsigned)er < (unsigned)TS && (unsigned)ec < (unsigned)TS;
     const int rb = er < H ? 0 : (er >= TS - H ? 2 : 1), cb = ec < H ? 0 : (ec >= TS - H ? 2 : 1);
@@ -284,7 +273,7 @@ __device__ __forceinline__ void k_classify(KSmem<TS, H>& S, int p, int lr, int l
         }
         oc = (cls << 12) | (unsigned)min(rank, 0xFFF);
     }
-    S.pcode[p] = (unsigned short)oc;
+    S.pw[p] = oc;
 }
 
 // Walls (reference serial.cpp:53-61), out of line and through shared memory: only tiles whose region touches a wall get here,
@@ -296,158 +285,304 @@ static __device__ __noinline__ void k_reflect_in_place(double2* pos, double2* ve
     *vel = v;
 }
 
-// One time step of the region in shared memory (everything between two __syncthreads of the kernel).
+// Are the cells of two particles the same or adjacent (the reference only ever compares a particle with the members of its
+// 3x3 cell neighbourhood, serial.cpp:102-117)?  Two particles within the cutoff practically always are; the test only decides
+// pairs that sit within a few ulps of two cell edges at once.  Returns the neighbour's visit rank as seen from `a`, or -1.
+__device__ __forceinline__ int k_neighbour_rank(const double2 a, const double2 c, int bincnt) {
+    const int dr = axis_cell(c.x, bincnt) - axis_cell(a.x, bincnt), dc = axis_cell(c.y, bincnt) - axis_cell(a.y, bincnt);
+    if (dr < -1 || dr > 1 || dc < -1 || dc > 1) return -1;
+    return visit_rank(dr, dc);
+}
 
-template <int TS, int H, bool kStoreAcc>
-static __device__ __forceinline__ void kstep_substep(int s, int b, bool last, int rbase, int cbase, bool at_wall, int bincnt, double size,
-                                                      int vlim_hi, double2* acc_tmp) {
+// ---- candidate search (once per tile) ---------------------------------------------------------------------------------------
+// Every loaded particle looks at the "earlier half" of its 5x5 cell neighbourhood -- the two rows above, the two cells to its
+// left, and the members of its own cell that follow it in the cell's list -- so that every unordered pair is met exactly once,
+// and lists the pairs within rs (cutoff + twice the distance a particle may travel in the remaining sub-steps of this launch,
+// which the speed check enforces): no other pair can come within the cutoff before the next launch.  The reference's 3x3
+// walk (serial.cpp:102-117) is the rs = cutoff special case; its cell structure is re-imposed exactly when a pair is evaluated.
+template <int TS, int H>
+static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int b, int n, int np0, double rs2) {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
-    constexpr int TW = D::TW, RW = D::RW, NW = D::NW;
-    extern __shared__ __align__(128) unsigned char k_smem_raw[];
-    KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
+    constexpr int TW = D::TW, RW = D::RW;
+    const int lane = threadIdx.x & 31;
+    const double2* posb = S.pos[b];
+    const unsigned short* next = S.u.t.next;
+    const int nch = (n + 31) >> 5;
+    // chunks of 32 particles are handed out dynamically (their cost varies with the local density); the warp reconverges
+    // after every chunk -- without the explicit __syncwarp the lanes drift apart and every later instruction is issued
+    // several times for a few lanes each
+#pragma unroll 1
+    for (;;) {
+        int ch = 0;
+        if (lane == 0) ch = k_atoms_add(&S.work, 1);
+        ch = __shfl_sync(0xffffffffu, ch, 0);
+        if (ch >= nch) break;
+        const int p = ch * 32 + lane;
+        if (p < n) {
+        const unsigned cc = S.pw[p];
+        S.pw[p] = 0u;   // from here on: the particle's force word
+        const int lr = (int)(cc >> 8), lc = (int)(cc & 0xFFu);
+        const double2 me = posb[p];
+        // occupancy of rows lr-2, lr-1 (five cells from column lc-2) and of row lr (columns lc-2, lc-1, and my own cell)
+        const unsigned* rb = S.u.t.bitmap + (lr - 2) * RW + ((lc - 2) >> 5);
+        const unsigned sh = (unsigned)(lc - 2) & 31u;
+        unsigned m = (__funnelshift_r(rb[0], rb[1], sh) & 31u) | ((__funnelshift_r(rb[RW], rb[RW + 1], sh) & 31u) << 8) |
+                     ((__funnelshift_r(rb[2 * RW], rb[2 * RW + 1], sh) & 3u) << 16);
+        const unsigned own_next = next[p];
+        if (own_next) m |= 1u << 18;   // members of my own cell that follow me in its list
+        const unsigned short* hcorner = S.u.t.head + (lr - 2) * TW + (lc - 2);
+#pragma unroll 1
+        while (m) {
+            const int k = __ffs((int)m) - 1;
+            m &= m - 1;
+            unsigned h = k == 18 ? own_next : (unsigned)hcorner[(k >> 3) * TW + (k & 7)];
+#pragma unroll 1
+            do {   // the occupancy bit guarantees a non-empty list
+                const unsigned j = h - 1u;
+                const double2 pj = posb[j];
+                h = next[j];
+                const double dx = __dsub_rn(pj.x, me.x), dy = __dsub_rn(pj.y, me.y);
+                const double r2 = pair_r2(dx, dy);
+                if (r2 <= rs2 && min((unsigned)p, j) < (unsigned)np0) {
+                    const int slot = k_atoms_add(&S.npairs, 1);
+                    if (slot < D::PCAP) S.u.t.pairs[slot] = (unsigned)p | (j << 16);
+                }
+            } while (h);
+        }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- a sub-step, first half: which listed pairs are within the cutoff now; their contributions ---------------------------------
+// The in-range pairs of a warp's share of the list are collected (two ballots, no atomics) and evaluated densely, one lane per
+// pair: the sqrt + divisions of reference serial.cpp:29-33 run once per PAIR (the second particle takes the exact negative).
+// Each particle's force word counts its in-range neighbours and remembers the first two evaluated pairs.
+template <int TS, int H>
+static __device__ __forceinline__ void k_flush_pairs(KSmem<TS, H>& S, const double2* posb, int wcnt, int np, int bincnt) {
+    using D = KDims<TS, H>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int gbase = 0;
+    if (lane == 0) gbase = atomicAdd(&S.ncon, wcnt);
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);
+    __syncwarp();
+    if (lane < wcnt) {
+        const unsigned ij = S.wlist[warp][lane];
+        const unsigned i = ij & 0xFFFFu, j = ij >> 16;
+        const double2 a = posb[i], c = posb[j];
+        const int g = gbase + lane;
+        const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
+        // two particles less than 0.9999 cells apart along both axes lie in the same or in adjacent cells (the computed cell
+        // index is off by far less than 1e-4 cells); the exact test only runs for the others
+        bool adjacent = true;
+        if (fmax(fabs(dx), fabs(dy)) > 0.9999 * kBin) adjacent = k_neighbour_rank(a, c, bincnt) >= 0;
+        if (g < D::NCON && adjacent) {
+            double cx, cy;
+            pair_contrib(dx, dy, pair_r2(dx, dy), cx, cy);
+            S.wres[g] = make_double2(cx, cy);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const unsigned q = side ? j : i;
+                if (q < (unsigned)np) {   // (a partner that is no longer processed only acts on the other one)
+                    const unsigned cnt = atomicAdd(&S.pw[q], 1u << kCntShift) >> kCntShift;
+                    const unsigned ref = (unsigned)g | (side ? kRefNeg : 0u);
+                    if (cnt < 2u) atomicOr(&S.pw[q], ref << (cnt * kRefBits));
+                    if (cnt >= 14u) atomicOr(&S.flags, kErrSmemOverflow);   // the 4-bit count would wrap: hand over
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int TS, int H>
+static __device__ __forceinline__ void k_pair_phase(KSmem<TS, H>& S, int b, int np, int nvalid, int bincnt) {
+    using C = KCfg<TS, H>;
+    using D = KDims<TS, H>;
+    constexpr int T = C::T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    bool too_fast = false;
-    {
-        const unsigned vb = (unsigned)(s + 1) << kIdxBits;   // entries of this sub-step are >= vb
-        const double2* posb = S.pos[b];
-        double2* posn = S.pos[b ^ 1];
-        const unsigned short* next = S.next[b];
-        const unsigned short* headh = reinterpret_cast<const unsigned short*>(S.u.t.head) + b;   // this parity's half of every head word
-        const unsigned* bm = S.u.t.bitmap[s];
-        const int np = S.nproc[s], nch = (np + 31) >> 5;
-        int wbase = 0;
-        // pass 1: candidate search, exact distance test
+    const double2* posb = S.pos[b];
+    const int npairs = min(S.npairs, D::PCAP);
+    int wcnt = 0;
 #pragma unroll 1
-        for (int ch = warp; ch < nch; ch += NW) {
-            const int p = ch * 32 + lane;
-            int fc = 0;
-            unsigned cand = 0;   // the last two in-range neighbours, 16 bits each
-            if (p < np) {
-                const int cc = S.ccode[p];
-                const int lr = cc >> 8, lc = cc & 0xFF;
-                const int cell = lr * TW + lc;
-                const double2 me = posb[p];
-                // 9 occupancy bits of the 3x3 neighbourhood, bit 8*(dr+1) + (dc+1)
-                const unsigned* rb = bm + (lr - 1) * RW + ((lc - 1) >> 5);
-                const unsigned sh = (unsigned)(lc - 1) & 31u;
-                unsigned m = 0;
-#pragma unroll
-                for (int dr = 0; dr < 3; ++dr) m |= (__funnelshift_r(rb[dr * RW], rb[dr * RW + 1], sh) & 7u) << (8 * dr);
-                if (headh[2 * cell] == (unsigned short)(vb | (unsigned)p) && next[p] < vb) m &= ~(1u << 9);   // alone in my own cell
-                const unsigned short* hcorner = headh + 2 * (cell - TW - 1);
-#pragma unroll 1
-                while (m) {
-                    const int k = __ffs((int)m) - 1;
-                    m &= m - 1;
-                    unsigned h = hcorner[(k >> 3) * (2 * TW) + 2 * (k & 7)];
-#pragma unroll 1
-                    do {   // the occupancy bit guarantees a non-empty list
-                        const unsigned j = h & kIdxMask;
-                        const double2 pj = posb[j];
-                        const unsigned hn = next[j];
-                        const double dx = __dsub_rn(pj.x, me.x), dy = __dsub_rn(pj.y, me.y);
-                        const double r2 = pair_r2(dx, dy);
-                        if (!(r2 > kCutoff2) && j != (unsigned)p) {
-                            cand = (cand << 16) | j;
-                            ++fc;
-                        }
-                        h = hn;
-                    } while (h >= vb);
-                }
-            }
-            // list the pairs of particles with one or two in-range neighbours: slots from two ballots, no atomics
-            const bool one = fc == 1 || fc == 2, two = fc == 2;
-            const unsigned m1 = __ballot_sync(0xffffffffu, one), m2 = __ballot_sync(0xffffffffu, two);
-            unsigned code = fc >= 3 ? 3u : 0u;
-            if (one) {
-                const int base = wbase + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
-                if (base + fc <= 32) {
-                    S.wij[warp][base] = (unsigned)p | (cand << 16);
-                    if (two) S.wij[warp][base + 1] = (unsigned)p | (cand & 0xFFFF0000u);
-                    code = (unsigned)fc | ((unsigned)base << 2);
-                } else {
-                    // no room: exact path.  A reserved entry below 32 must still be well formed for the evaluation:
-                    // a self pair (distance 0) contributes nothing.
-                    if (base < 32) S.wij[warp][base] = (unsigned)p | ((unsigned)p << 16);
-                    code = 3u;
-                }
-            }
-            wbase += __popc(m1) + __popc(m2);
-            if (p < np) S.pcode[p] = (unsigned short)code;
-        }
-        __syncwarp();
-        // dense evaluation of the warp's pairs: one lane per pair
-        if (lane < min(wbase, 32)) {
-            const unsigned ij = S.wij[warp][lane];
-            const double2 a = posb[ij & 0xFFFFu], c = posb[ij >> 16];
+    for (int base = warp * 32; base < npairs; base += T) {
+        const int e = base + lane;
+        bool hit = false;
+        unsigned ij = 0;
+        if (e < npairs) {
+            ij = S.u.t.pairs[e];
+            const unsigned i = ij & 0xFFFFu, j = ij >> 16;
+            const double2 a = posb[i], c = posb[j];
             const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
             const double r2 = pair_r2(dx, dy);
-            double cx = 0.0, cy = 0.0;
-            if (!(r2 > kCutoff2) && r2 != 0.0) pair_contrib(dx, dy, r2, cx, cy);
-            S.wres[warp][lane] = make_double2(cx, cy);
+            // a pair matters while one of the two is still processed and both still carry valid positions; pairs at
+            // distance exactly 0 contribute coef * 0 = -0, which a sum from +0 absorbs (serial.cpp:107 meets the self pair)
+            hit = !(r2 > kCutoff2) && r2 != 0.0 && min(i, j) < (unsigned)np && max(i, j) < (unsigned)nvalid;
         }
-        __syncwarp();
-        // pass 2: sum, move, speed check, next cell
-#pragma unroll 1
-        for (int ch = warp; ch < nch; ch += NW) {
-            const int p = ch * 32 + lane;
-            if (p < np) {
-                // (the buffer parity is laundered through an empty asm: the addresses derived from it are then recomputed per
-                // chunk -- two or three integer instructions each -- instead of being spilled to local memory across the loop)
-                int bl = b;
-                asm volatile("" : "+r"(bl));
-                const double2* posb = S.pos[bl];
-                double2* posn = S.pos[bl ^ 1];
-                const unsigned code = S.pcode[p], fc = code & 3u;
-                const double2 me = posb[p];
-                double2 v = S.vel[p];
-                double x = me.x, y = me.y, ax = 0.0, ay = 0.0;
-                if (fc == 3u) {
-                    const int cc = S.ccode[p];
-                    const double2 a = kslow_force<TS, H>(S, b, vb, p, (cc >> 8) * TW + (cc & 0xFF));
-                    ax = a.x;
-                    ay = a.y;
-                } else if (fc != 0u) {
-                    const double2 c0_ = S.wres[warp][code >> 2];
-                    ax = __dadd_rn(ax, c0_.x);
-                    ay = __dadd_rn(ay, c0_.y);
-                    if (fc == 2u) {
-                        const double2 c1_ = S.wres[warp][(code >> 2) + 1];
-                        ax = __dadd_rn(ax, c1_.x);
-                        ay = __dadd_rn(ay, c1_.y);
-                    }
-                }
-                // integrate (reference serial.cpp:46-51); walls (serial.cpp:53-61) only where the loaded region touches one:
-                // elsewhere a particle that reaches a wall has left the trusted part of the region anyway
-                v.x = __dadd_rn(v.x, __dmul_rn(ax, kDt));
-                v.y = __dadd_rn(v.y, __dmul_rn(ay, kDt));
-                x = __dadd_rn(x, __dmul_rn(v.x, kDt));
-                y = __dadd_rn(y, __dmul_rn(v.y, kDt));
-                too_fast |= max(__double2hiint(v.x) & 0x7FFFFFFF, __double2hiint(v.y) & 0x7FFFFFFF) >= vlim_hi;
-                posn[p] = make_double2(x, y);
-                S.vel[p] = v;
-                if (at_wall) {
-                    k_reflect_in_place(&posn[p], &S.vel[p], size);
-                    const double2 q = posn[p];
-                    x = q.x;
-                    y = q.y;
-                }
-                int lr, lc;
-                k_table_cell<TW>(x, y, rbase, cbase, at_wall, bincnt, lr, lc);
-                if (!last) {
-                    k_bin_particle<TS, H>(S, p, lr, lc, bl ^ 1, (unsigned)(s + 2), S.u.t.bitmap[s + 1]);
-                } else {
-                    k_classify<TS, H>(S, p, lr, lc);
-                    if (kStoreAcc) acc_tmp[p] = make_double2(ax, ay);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            if (wcnt + __popc(bal) > 32) {
+                k_flush_pairs<TS, H>(S, posb, wcnt, np, bincnt);
+                wcnt = 0;
+            }
+            if (hit) S.wlist[warp][wcnt + __popc(bal & lt_mask)] = ij;
+            wcnt += __popc(bal);
+        }
+    }
+    if (wcnt) k_flush_pairs<TS, H>(S, posb, wcnt, np, bincnt);
+}
+
+// Rare path: a particle with three or more in-range neighbours.  The whole warp scans the pair list for its partners; the owner
+// lane then sums their contributions in ascending (reference cell-visit rank, x, y) order -- the order the oracle uses
+// (oracle/psim_oracle.c, "Summation order").
+static __device__ __noinline__ double2 kslow_sum(const double2* xy, unsigned short* nb, int n, int i) {
+    auto less = [&](unsigned u, unsigned v) {
+        if ((u >> 12) != (v >> 12)) return (u >> 12) < (v >> 12);
+        const double2 pu = xy[u & 0xFFFu], pv = xy[v & 0xFFFu];
+        if (pu.x != pv.x) return pu.x < pv.x;
+        return pu.y < pv.y;
+    };
+    for (int a = 1; a < n; ++a) {
+        const unsigned cur = nb[a];
+        int q = a;
+        while (q > 0 && less(cur, nb[q - 1])) {
+            nb[q] = nb[q - 1];
+            --q;
+        }
+        nb[q] = (unsigned short)cur;
+    }
+    const double2 me = xy[i];
+    double sx = 0.0, sy = 0.0;
+    for (int a = 0; a < n; ++a) {
+        const double2 pj = xy[nb[a] & 0xFFFu];
+        const double dx = __dsub_rn(pj.x, me.x), dy = __dsub_rn(pj.y, me.y);
+        double cx, cy;
+        pair_contrib(dx, dy, pair_r2(dx, dy), cx, cy);
+        sx = __dadd_rn(sx, cx);
+        sy = __dadd_rn(sy, cy);
+    }
+    return make_double2(sx, sy);
+}
+
+template <int TS, int H>
+static __device__ __noinline__ double2 kslow_force(KSmem<TS, H>& S, int b, unsigned slow, int p, int nvalid, int bincnt) {
+    using D = KDims<TS, H>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double2* xy = S.pos[b];
+    const int npairs = min(S.npairs, D::PCAP);
+    double2 out = make_double2(0.0, 0.0);
+    while (slow) {
+        const int leader = __ffs((int)slow) - 1;
+        slow &= slow - 1;
+        const unsigned i = (unsigned)__shfl_sync(0xffffffffu, p, leader);
+        const double2 me = xy[i];
+        int cnt = 0;
+        for (int base = 0; base < npairs; base += 32) {
+            const int e = base + lane;
+            bool hit = false;
+            unsigned ent = 0;
+            if (e < npairs) {
+                const unsigned ij = S.u.t.pairs[e];
+                const unsigned a = ij & 0xFFFFu, c = ij >> 16;
+                if ((a == i || c == i) && max(a, c) < (unsigned)nvalid) {
+                    const unsigned o = a == i ? c : a;
+                    const double2 po = xy[o];
+                    const double dx = __dsub_rn(po.x, me.x), dy = __dsub_rn(po.y, me.y);
+                    const double r2 = pair_r2(dx, dy);
+                    const int rank = k_neighbour_rank(me, po, bincnt);
+                    hit = !(r2 > kCutoff2) && r2 != 0.0 && rank >= 0;
+                    ent = ((unsigned)max(rank, 0) << 12) | o;
                 }
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int k = cnt + __popc(bal & lt_mask);
+                if (k < kSlowMax) S.wslow[warp][k] = (unsigned short)ent;
+            }
+            cnt += __popc(bal);
         }
-        // diagnostics and the speed flag go straight to shared memory: nothing stays live across the sub-steps
-        if (__any_sync(0xffffffffu, too_fast) && lane == 0) atomicOr(&S.flags, kErrSpeedBound);
-        if (lane == 0 && wbase > S.hw_pairs) atomicMax(&S.hw_pairs, wbase);
+        __syncwarp();
+        if (lane == leader) {
+            if (cnt > kSlowMax) atomicOr(&S.flags, kErrSmemOverflow);   // denser than any physical configuration: hand over
+            out = kslow_sum(xy, S.wslow[warp], min(cnt, kSlowMax), (int)i);
+        }
+        __syncwarp();
     }
+    return out;
+}
+
+// ---- a sub-step, second half: sum, move, speed check; after the last one: final cell -> class ---------------------------------
+template <int TS, int H, bool kStoreAcc>
+static __device__ __forceinline__ void k_move_phase(KSmem<TS, H>& S, int b, int np, int nvalid, bool last, int rbase, int cbase, bool at_wall,
+                                                    int bincnt, double size, double vlim2, double2* acc_tmp) {
+    using C = KCfg<TS, H>;
+    using D = KDims<TS, H>;
+    constexpr int TW = D::TW, NW = D::NW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double2* posb = S.pos[b];
+    double2* posn = S.pos[b ^ 1];
+    const int nch = (np + 31) >> 5;
+    bool too_fast = false;
+#pragma unroll 1
+    for (int ch = warp; ch < nch; ch += NW) {
+        const int p = ch * 32 + lane;
+        const unsigned w = p < np ? S.pw[p] : 0u;
+        const unsigned cnt = w >> kCntShift;
+        double ax = 0.0, ay = 0.0;
+        const unsigned slow = __ballot_sync(0xffffffffu, cnt >= 3u);
+        if (slow) {
+            const double2 a = kslow_force<TS, H>(S, b, slow, p, nvalid, bincnt);
+            if (cnt >= 3u) {
+                ax = a.x;
+                ay = a.y;
+            }
+        }
+        if (p < np) {
+            if (cnt == 1u || cnt == 2u) {
+                // (the pair's second particle takes the exact negative: flip the sign bit)
+                auto signed_of = [](double v, unsigned ref) {
+                    return __hiloint2double(__double2hiint(v) ^ (int)((ref & kRefNeg) << 18), __double2loint(v));
+                };
+                const double2 c0 = S.wres[w & (kRefNeg - 1u)];
+                ax = __dadd_rn(ax, signed_of(c0.x, w));
+                ay = __dadd_rn(ay, signed_of(c0.y, w));
+                if (cnt == 2u) {
+                    const unsigned w1 = w >> kRefBits;
+                    const double2 c1 = S.wres[w1 & (kRefNeg - 1u)];
+                    ax = __dadd_rn(ax, signed_of(c1.x, w1));
+                    ay = __dadd_rn(ay, signed_of(c1.y, w1));
+                }
+            }
+            // integrate (reference serial.cpp:46-51); walls (serial.cpp:53-61) only where the loaded region touches one:
+            // elsewhere a particle that reaches a wall has left the trusted part of the region anyway
+            const double2 me = posb[p];
+            double2 v = S.vel[p];
+            v.x = __dadd_rn(v.x, __dmul_rn(ax, kDt));
+            v.y = __dadd_rn(v.y, __dmul_rn(ay, kDt));
+            double x = __dadd_rn(me.x, __dmul_rn(v.x, kDt)), y = __dadd_rn(me.y, __dmul_rn(v.y, kDt));
+            too_fast |= !(__fma_rn(v.x, v.x, __dmul_rn(v.y, v.y)) < vlim2);
+            posn[p] = make_double2(x, y);
+            S.vel[p] = v;
+            if (at_wall) {
+                k_reflect_in_place(&posn[p], &S.vel[p], size);
+                const double2 q = posn[p];
+                x = q.x;
+                y = q.y;
+            }
+            if (!last) {
+                S.pw[p] = 0u;
+            } else {
+                int lr, lc;
+                k_table_cell<TW>(x, y, rbase, cbase, at_wall, bincnt, lr, lc);
+                k_classify<TS, H>(S, p, lr, lc);
+                if (kStoreAcc) acc_tmp[p] = make_double2(ax, ay);
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, too_fast) && lane == 0) atomicOr(&S.flags, kErrSpeedBound);
 }
 
 
@@ -466,7 +601,6 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nsub = P.nsub;
-    const int vlim_hi = __double2hiint(P.vlim);   // speeds are compared by the high words of their absolute values
     const int G = gridDim.x;
 
     if (tid == 0) {
@@ -557,8 +691,9 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
     for (int it = 0; cur.t < P.ntiles; ++it, advance(cur)) {
         const int q = it & 1, t = cur.t;
         const int lrow = cur.lrow, tc = cur.tc;
-        const int rbase = (P.tr_base + lrow) * TS - H - 1, cbase = tc * TS - H - 1;   // global cell of table row / column 0
-        const bool at_wall = rbase + 1 <= 0 || cbase + 1 <= 0 || rbase + TW - 2 >= P.bincnt - 1 || cbase + TW - 2 >= P.bincnt - 1;
+        const int rbase = (P.tr_base + lrow) * TS - H - kGuard, cbase = tc * TS - H - kGuard;   // global cell of table row / column 0
+        const bool at_wall = rbase + kGuard <= 0 || cbase + kGuard <= 0 || rbase + TW - 1 - kGuard >= P.bincnt - 1 ||
+                             cbase + TW - 1 - kGuard >= P.bincnt - 1;
 
         // a particle's table cell: its exact cell, clamped to the box (reference semantics for x == size) and to the table
         // interior (only particles whose computed state is already worthless can leave the loaded region)
@@ -587,7 +722,7 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                 hvel = S.u.vland[n_own + tid];
                 int lr, lc;
                 table_cell(hpos.x, hpos.y, lr, lc);
-                const int er = lr - (H + 1), ec = lc - (H + 1);
+                const int er = lr - (H + kGuard), ec = lc - (H + kGuard);
                 const int dr = er < 0 ? -er : (er >= TS ? er - TS + 1 : 0), dc = ec < 0 ? -ec : (ec >= TS ? ec - TS + 1 : 0);
                 hring = min(max(max(dr, dc), 1), H);
                 hrank = atomicAdd(&S.ringcnt[hring], 1);
@@ -615,11 +750,12 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
 #pragma unroll
         for (int k = 0; k < kIdRegs; ++k)
             if (tid + k * T < n_own) S.id[tid + k * T] = idreg[k];
-        {   // wipe the cell table and the occupancy maps
+        {   // wipe the cell table and the occupancy map
             uint4* hq = reinterpret_cast<uint4*>(S.u.t.head);
-            for (int c = tid; c < D::NC4 / 4; c += T) hq[c] = make_uint4(0u, 0u, 0u, 0u);
-            uint4* bq = reinterpret_cast<uint4*>(&S.u.t.bitmap[0][0]);
-            for (int c = tid; c < C::KMAX * D::BM / 4; c += T) bq[c] = make_uint4(0u, 0u, 0u, 0u);
+            for (int c = tid; c < D::NC8 / 8; c += T) hq[c] = make_uint4(0u, 0u, 0u, 0u);
+            uint4* bq = reinterpret_cast<uint4*>(S.u.t.bitmap);
+            for (int c = tid; c < D::BM / 4; c += T) bq[c] = make_uint4(0u, 0u, 0u, 0u);
+            if (tid == 0) S.npairs = S.ncon = S.work = 0;
         }
         __syncthreads();
 
@@ -635,17 +771,32 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                 const double2 a = S.pos[b0][p];
                 int lr, lc;
                 table_cell(a.x, a.y, lr, lc);
-                k_bin_particle<TS, H>(S, p, lr, lc, b0, 1u, S.u.t.bitmap[0]);
+                k_bin_particle<TS, H>(S, p, lr, lc);
             }
         }
         k_fence_proxy_async();   // (only matters for nsub == 0: the barrier below is then the last one before the next bulk copies)
         __syncthreads();
 
-        // ---- the fused time steps ----------------------------------------------------------------------------------
+        // ---- candidate pairs of the whole launch, then the fused time steps ---------------------------------------------
+        if (nsub > 0) {
+            k_search<TS, H>(S, b0, n, S.nproc[0], P.rs2);
+            __syncthreads();
+            if (tid == 0) {
+                if (S.npairs > D::PCAP) atomicOr(&S.flags, kErrSmemOverflow);
+                S.hw_pairs = max(S.hw_pairs, S.npairs);
+            }
+        }
         for (int s = 0; s < nsub; ++s) {
-            kstep_substep<TS, H, kStoreAcc>(s, (b0 + s) & 1, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size, vlim_hi,
-                                            P.acc_tmp + (size_t)blockIdx.x * NMAX);
-            if (s + 1 == nsub) k_fence_proxy_async();   // my accesses to the cell table and the free position buffer precede the next tile's bulk copies
+            const int b = (b0 + s) & 1, np = S.nproc[s], nvalid = s == 0 ? n : S.nproc[s - 1];
+            k_pair_phase<TS, H>(S, b, np, nvalid, P.bincnt);
+            __syncthreads();
+            if (tid == 0) {
+                if (S.ncon > D::NCON) atomicOr(&S.flags, kErrSmemOverflow);
+                S.ncon = 0;
+            }
+            k_move_phase<TS, H, kStoreAcc>(S, b, np, nvalid, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size, P.vlim2,
+                                           P.acc_tmp + (size_t)blockIdx.x * NMAX);
+            if (s + 1 == nsub) k_fence_proxy_async();   // my accesses to the search tables and the free position buffer precede the next tile's bulk copies
             __syncthreads();
         }
 
@@ -703,7 +854,7 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
             const bool sorted = P.ringsort && nsub > 0 && S.ncount[q] - n_own_ <= T;
 #pragma unroll 1
             for (int p = tid; p < nfin; p += TS_) {
-                const unsigned oc = S.pcode[p];
+                const unsigned oc = S.pw[p];
                 if (oc == kNoOwner) continue;
                 const unsigned cls = oc >> 12;
                 const int d = S.segoff[cls] + (int)(oc & 0xFFFu);
@@ -1008,9 +1159,20 @@ static int klaunch_rows(psim_sim* sim, KstepEngine* e, int parity_in, int nsub, 
     if (allow_peer && sim->nranks > 1) P.acc_tmp += (size_t)e->grid_cap * e->nmax;   // the boundary launch's own scratch
     P.nsub = nsub;
     P.seq = seq;
-    // displacement bound per step that H halo cells allow for nsub fused steps, with a 2 % margin for the rounding of the
-    // region arithmetic: d = (H - nsub) / nsub cells  ->  |v| <= d * 0.01 / dt
-    P.vlim = nsub > 0 ? 0.98 * ((double)(e->h - nsub) / nsub) * PSIM_BIN_SIZE / PSIM_DT : 1e300;
+    // Speed bound of the launch (2 % margins for the rounding of the region arithmetic).  Halo: H cells allow nsub fused steps
+    // a displacement of d = (H - nsub) / nsub cells per step.  Candidate list: it is built from the positions at the first
+    // sub-step with radius rs < 2 cells (the search covers the 5x5 cell neighbourhood) and must contain every pair that comes
+    // within the cutoff in the nsub - 1 steps that follow: rs = cutoff + 2 (nsub - 1) v dt.
+    {
+        double v = 1e300, rs = PSIM_CUTOFF;
+        if (nsub > 0) v = 0.98 * ((double)(e->h - nsub) / nsub) * PSIM_BIN_SIZE / PSIM_DT;
+        if (nsub > 1) {
+            v = std::min(v, 0.98 * PSIM_BIN_SIZE / (2.0 * (nsub - 1) * PSIM_DT));
+            rs = PSIM_CUTOFF + 2.0 * (nsub - 1) * v * PSIM_DT * (1.0 + 1e-9);
+        }
+        P.vlim2 = v * v;
+        P.rs2 = rs * rs * (1.0 + 1e-12);
+    }
     switch (e->ts * 8 + e->h) {
         case 16 * 8 + 3: return klaunch<16, 3>(sim, e, P, store_acc, s);
         case 16 * 8 + 4: return klaunch<16, 4>(sim, e, P, store_acc, s);
