@@ -125,7 +125,7 @@ template <int TS, int H> struct __align__(16) KSmem {
         double2 vland[C::NMAX];              // landing zone of the NEXT tile's velocities while this tile is stored (TMA destination)
     } u;
     unsigned pw[C::NMAX];                    // bin -> search: table row << 8 | column;  sub-steps: force word;  store phase: class << 12 | rank
-    unsigned wlist[D::NW][32];               // per warp: in-range pairs waiting for their dense evaluation
+    unsigned inlist[D::NCON];                // the in-range pairs of the current sub-step, waiting for their dense evaluation
     unsigned short wslow[D::NW][kSlowMax];   // per warp: neighbours of a particle on the canonical-order path (rank << 12 | slot)
     int id[C::CAP];                          // ids of the tile's own stripe (halo particles that end up inside fetch theirs at store time)
     unsigned short horig[C::T];              // halo particle -> its shared slot before the ring sort (id look-up at store time)
@@ -278,11 +278,16 @@ __device__ __forceinline__ void k_classify(KSmem<TS, H>& S, int p, int lr, int l
 
 // Walls (reference serial.cpp:53-61), out of line and through shared memory: only tiles whose region touches a wall get here,
 // and keeping the bounce loops out of pass 2 keeps their registers out of it too.
-static __device__ __noinline__ void k_reflect_in_place(double2* pos, double2* vel, double size) {
-    double2 q = *pos, v = *vel;
+// (Out-of-line functions name the shared-memory block themselves instead of taking pointers into it: a generic pointer to
+// shared memory makes the compiler rebuild the CTA's shared window address -- S2R SR_CgaCtaId -- all over the hot loops.)
+template <int TS, int H>
+static __device__ __noinline__ void k_reflect_in_place(int bn, int p, double size) {
+    extern __shared__ __align__(128) unsigned char k_smem_raw[];
+    KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
+    double2 q = S.pos[bn][p], v = S.vel[p];
     reflect_particle(q.x, q.y, v.x, v.y, size);
-    *pos = q;
-    *vel = v;
+    S.pos[bn][p] = q;
+    S.vel[p] = v;
 }
 
 // Are the cells of two particles the same or adjacent (the reference only ever compares a particle with the members of its
@@ -345,8 +350,13 @@ static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int b, int n, i
                 const double dx = __dsub_rn(pj.x, me.x), dy = __dsub_rn(pj.y, me.y);
                 const double r2 = pair_r2(dx, dy);
                 if (r2 <= rs2 && min((unsigned)p, j) < (unsigned)np0) {
+                    const unsigned ij = (unsigned)p | (j << 16);
                     const int slot = k_atoms_add(&S.npairs, 1);
-                    if (slot < D::PCAP) S.u.t.pairs[slot] = (unsigned)p | (j << 16);
+                    if (slot < D::PCAP) S.u.t.pairs[slot] = ij;
+                    if (!(r2 > kCutoff2) && r2 != 0.0) {   // in range right now: the first sub-step evaluates it
+                        const int g = k_atoms_add(&S.ncon, 1);
+                        if (g < D::NCON) S.inlist[g] = ij;
+                    }
                 }
             } while (h);
         }
@@ -356,28 +366,61 @@ static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int b, int n, i
 }
 
 // ---- a sub-step, first half: which listed pairs are within the cutoff now; their contributions ---------------------------------
-// The in-range pairs of a warp's share of the list are collected (two ballots, no atomics) and evaluated densely, one lane per
-// pair: the sqrt + divisions of reference serial.cpp:29-33 run once per PAIR (the second particle takes the exact negative).
-// Each particle's force word counts its in-range neighbours and remembers the first two evaluated pairs.
+// k_pair_check collects the in-range pairs of the whole tile in one list (the first sub-step gets them from the search itself);
+// after a barrier k_pair_eval evaluates them densely, one lane per pair, full warps: the sqrt + divisions of reference
+// serial.cpp:29-33 run once per PAIR (the second particle takes the exact negative).  Each particle's force word counts its
+// in-range neighbours and remembers the first two evaluated pairs.
 template <int TS, int H>
-static __device__ __forceinline__ void k_flush_pairs(KSmem<TS, H>& S, const double2* posb, int wcnt, int np, int bincnt) {
+static __device__ __forceinline__ void k_pair_check(KSmem<TS, H>& S, int b, int np, int nvalid) {
+    using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
+    constexpr int T = C::T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int gbase = 0;
-    if (lane == 0) gbase = atomicAdd(&S.ncon, wcnt);
-    gbase = __shfl_sync(0xffffffffu, gbase, 0);
-    __syncwarp();
-    if (lane < wcnt) {
-        const unsigned ij = S.wlist[warp][lane];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int npairs = min(S.npairs, D::PCAP);
+#pragma unroll 1
+    for (int base = warp * 32; base < npairs; base += T) {
+        const int e = base + lane;
+        bool hit = false;
+        unsigned ij = 0;
+        if (e < npairs) {
+            ij = S.u.t.pairs[e];
+            const unsigned i = ij & 0xFFFFu, j = ij >> 16;
+            const double2 a = S.pos[b][i], c = S.pos[b][j];
+            const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
+            const double r2 = pair_r2(dx, dy);
+            // a pair matters while one of the two is still processed and both still carry valid positions; pairs at
+            // distance exactly 0 contribute coef * 0 = -0, which a sum from +0 absorbs (serial.cpp:107 meets the self pair)
+            hit = !(r2 > kCutoff2) && r2 != 0.0 && min(i, j) < (unsigned)np && max(i, j) < (unsigned)nvalid;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            int gbase = 0;
+            if (lane == 0) gbase = atomicAdd(&S.ncon, __popc(bal));
+            gbase = __shfl_sync(0xffffffffu, gbase, 0);
+            const int g = gbase + __popc(bal & lt_mask);
+            if (hit && g < D::NCON) S.inlist[g] = ij;
+        }
+    }
+}
+
+template <int TS, int H>
+static __device__ __forceinline__ void k_pair_eval(KSmem<TS, H>& S, int b, int np, int bincnt) {
+    using C = KCfg<TS, H>;
+    using D = KDims<TS, H>;
+    const double2* posb = S.pos[b];
+    const int ncon = min(S.ncon, D::NCON);
+#pragma unroll 1
+    for (int g = threadIdx.x; g < ncon; g += C::T) {
+        const unsigned ij = S.inlist[g];
         const unsigned i = ij & 0xFFFFu, j = ij >> 16;
         const double2 a = posb[i], c = posb[j];
-        const int g = gbase + lane;
         const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
         // two particles less than 0.9999 cells apart along both axes lie in the same or in adjacent cells (the computed cell
         // index is off by far less than 1e-4 cells); the exact test only runs for the others
         bool adjacent = true;
         if (fmax(fabs(dx), fabs(dy)) > 0.9999 * kBin) adjacent = k_neighbour_rank(a, c, bincnt) >= 0;
-        if (g < D::NCON && adjacent) {
+        if (adjacent) {
             double cx, cy;
             pair_contrib(dx, dy, pair_r2(dx, dy), cx, cy);
             S.wres[g] = make_double2(cx, cy);
@@ -393,51 +436,12 @@ static __device__ __forceinline__ void k_flush_pairs(KSmem<TS, H>& S, const doub
             }
         }
     }
-    __syncwarp();
-}
-
-template <int TS, int H>
-static __device__ __forceinline__ void k_pair_phase(KSmem<TS, H>& S, int b, int np, int nvalid, int bincnt) {
-    using C = KCfg<TS, H>;
-    using D = KDims<TS, H>;
-    constexpr int T = C::T;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const double2* posb = S.pos[b];
-    const int npairs = min(S.npairs, D::PCAP);
-    int wcnt = 0;
-#pragma unroll 1
-    for (int base = warp * 32; base < npairs; base += T) {
-        const int e = base + lane;
-        bool hit = false;
-        unsigned ij = 0;
-        if (e < npairs) {
-            ij = S.u.t.pairs[e];
-            const unsigned i = ij & 0xFFFFu, j = ij >> 16;
-            const double2 a = posb[i], c = posb[j];
-            const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
-            const double r2 = pair_r2(dx, dy);
-            // a pair matters while one of the two is still processed and both still carry valid positions; pairs at
-            // distance exactly 0 contribute coef * 0 = -0, which a sum from +0 absorbs (serial.cpp:107 meets the self pair)
-            hit = !(r2 > kCutoff2) && r2 != 0.0 && min(i, j) < (unsigned)np && max(i, j) < (unsigned)nvalid;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (bal) {
-            if (wcnt + __popc(bal) > 32) {
-                k_flush_pairs<TS, H>(S, posb, wcnt, np, bincnt);
-                wcnt = 0;
-            }
-            if (hit) S.wlist[warp][wcnt + __popc(bal & lt_mask)] = ij;
-            wcnt += __popc(bal);
-        }
-    }
-    if (wcnt) k_flush_pairs<TS, H>(S, posb, wcnt, np, bincnt);
 }
 
 // Rare path: a particle with three or more in-range neighbours.  The whole warp scans the pair list for its partners; the owner
 // lane then sums their contributions in ascending (reference cell-visit rank, x, y) order -- the order the oracle uses
 // (oracle/psim_oracle.c, "Summation order").
-static __device__ __noinline__ double2 kslow_sum(const double2* xy, unsigned short* nb, int n, int i) {
+static __device__ __forceinline__ double2 kslow_sum(const double2* xy, unsigned short* nb, int n, int i) {
     auto less = [&](unsigned u, unsigned v) {
         if ((u >> 12) != (v >> 12)) return (u >> 12) < (v >> 12);
         const double2 pu = xy[u & 0xFFFu], pv = xy[v & 0xFFFu];
@@ -467,8 +471,10 @@ static __device__ __noinline__ double2 kslow_sum(const double2* xy, unsigned sho
 }
 
 template <int TS, int H>
-static __device__ __noinline__ double2 kslow_force(KSmem<TS, H>& S, int b, unsigned slow, int p, int nvalid, int bincnt) {
+static __device__ __noinline__ double2 kslow_force(int b, unsigned slow, int p, int nvalid, int bincnt) {
     using D = KDims<TS, H>;
+    extern __shared__ __align__(128) unsigned char k_smem_raw[];
+    KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const double2* xy = S.pos[b];
@@ -534,7 +540,7 @@ static __device__ __forceinline__ void k_move_phase(KSmem<TS, H>& S, int b, int 
         double ax = 0.0, ay = 0.0;
         const unsigned slow = __ballot_sync(0xffffffffu, cnt >= 3u);
         if (slow) {
-            const double2 a = kslow_force<TS, H>(S, b, slow, p, nvalid, bincnt);
+            const double2 a = kslow_force<TS, H>(b, slow, p, nvalid, bincnt);
             if (cnt >= 3u) {
                 ax = a.x;
                 ay = a.y;
@@ -567,7 +573,7 @@ static __device__ __forceinline__ void k_move_phase(KSmem<TS, H>& S, int b, int 
             posn[p] = make_double2(x, y);
             S.vel[p] = v;
             if (at_wall) {
-                k_reflect_in_place(&posn[p], &S.vel[p], size);
+                k_reflect_in_place<TS, H>(b ^ 1, p, size);
                 const double2 q = posn[p];
                 x = q.x;
                 y = q.y;
@@ -781,17 +787,19 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
         if (nsub > 0) {
             k_search<TS, H>(S, b0, n, S.nproc[0], P.rs2);
             __syncthreads();
-            if (tid == 0) {
-                if (S.npairs > D::PCAP) atomicOr(&S.flags, kErrSmemOverflow);
-                S.hw_pairs = max(S.hw_pairs, S.npairs);
-            }
+            if (tid == 0 && S.npairs > D::PCAP) atomicOr(&S.flags, kErrSmemOverflow);
         }
         for (int s = 0; s < nsub; ++s) {
             const int b = (b0 + s) & 1, np = S.nproc[s], nvalid = s == 0 ? n : S.nproc[s - 1];
-            k_pair_phase<TS, H>(S, b, np, nvalid, P.bincnt);
+            if (s > 0) {   // (the first sub-step's in-range pairs come from the search)
+                k_pair_check<TS, H>(S, b, np, nvalid);
+                __syncthreads();
+            }
+            k_pair_eval<TS, H>(S, b, np, P.bincnt);
             __syncthreads();
             if (tid == 0) {
                 if (S.ncon > D::NCON) atomicOr(&S.flags, kErrSmemOverflow);
+                S.hw_pairs = max(S.hw_pairs, S.ncon);
                 S.ncon = 0;
             }
             k_move_phase<TS, H, kStoreAcc>(S, b, np, nvalid, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size, P.vlim2,
