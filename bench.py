@@ -117,6 +117,24 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(torch, local):
+    """Pin this process to the CPUs next to its GPU (what `numactl` does in a production launch) so that the pinned host array
+    the end-to-end region copies from / to is first touched on the GPU's NUMA node.  Returns the previous affinity mask (restored
+    before the CPU baseline runs, which must see every host core), or None when NVML cannot tell."""
+    try:
+        import pynvml
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        try:   # CUDA_VISIBLE_DEVICES may renumber the devices: go by UUID
+            handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{torch.cuda.get_device_properties(local).uuid}".encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return before
+    except Exception:   # no NVML, no permission, unknown topology: run unbound
+        return None
+
+
 def run_reference_harness(n, seed, steps, warmup, threads=None):
     if not os.path.exists(REF_HARNESS):
         raise FileNotFoundError(f"{REF_HARNESS} missing (built by `make -C oracle ref` in the build container)")
@@ -224,6 +242,7 @@ def main():
 
     n = args.particles * (world if args.scaling == "weak" else 1)
     size = pkg.box_size(n)
+    affinity_before = bind_near_gpu(torch, local)
     engine = {"auto": pkg.ENGINE_AUTO, "kstep": pkg.ENGINE_KSTEP, "tiled": pkg.ENGINE_TILED, "cellsort": pkg.ENGINE_CELLSORT}[args.engine]
 
     host = torch.empty((n, 6), dtype=torch.float64, pin_memory=True)
@@ -372,7 +391,9 @@ def main():
                    "l2": "state (>= 640 MB per GPU at 20 M) larger than the 126 MB L2; no flush needed" if per_gpu_particles >= 4e6
                          else "state fits L2: the HBM roofline fraction is not meaningful at this size",
                    "accel_store": "ax, ay materialised for the last step of the batch (the reference drivers never read them)",
-                   "device_bytes": info["device_bytes"]},
+                   "device_bytes": info["device_bytes"],
+                   "host_affinity": "bound to the GPU's NUMA node (NVML) while the pinned host array is allocated and copied"
+                                    if affinity_before is not None else "unbound"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None,
@@ -394,6 +415,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if affinity_before is not None:
+        os.sched_setaffinity(0, affinity_before)   # the CPU baseline below uses every host core
     if world == 1 and not args.no_cpu_baseline:
         try:
             r, kind, what = cpu_reference(n, args.seed, args.cpu_sample_steps, 1)

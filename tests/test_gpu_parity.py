@@ -252,6 +252,56 @@ def test_pair_list_overflow_takes_the_exact_path(pkg, oracle, engine):
     sim.close()
 
 
+@pytest.mark.parametrize("engine", ["kstep16", "kstep32", "kstep64"])
+def test_kstep_canonical_order_path_in_fused_launches(pkg, oracle, engine):
+    """Particles with three or more in-range neighbours INSIDE a fused 3-step launch: the kstep kernel counts a particle's
+    in-range pairs in its force word and, from three on, collects the partners from the tile's candidate-pair list and sums them
+    in the oracle's (cell-visit rank, x, y) order.  Hexagons at 0.9 cutoff spacing (every rim particle has three neighbours, the
+    centre six), stepped in batches of three so that the pairs come from the list built at the first sub-step."""
+    size = box_size(4000)
+    pts = []
+    for cx, cy, rot in [(0.305, 0.412, 0.1), (0.638, 0.642, 0.7), (0.9997, 0.3203, 1.3)]:   # (the second straddles 64-cell tiles)
+        pts.append((cx, cy))
+        pts += [(cx + 0.009 * np.cos(rot + k * np.pi / 3), cy + 0.009 * np.sin(rot + k * np.pi / 3)) for k in range(6)]
+    parts = np.zeros((len(pts), 6))
+    parts[:, :2] = np.array(pts)
+    parts[:, 2] = 0.05 * np.cos(np.arange(len(pts)))
+    parts[:, 3] = 0.05 * np.sin(3 * np.arange(len(pts)))
+    want = parts.copy()
+    sim = make_sim(pkg, parts, size, engine)
+    for _ in range(4):
+        oracle.step(want, size, 3)
+        got = sim.step(3).sync().read_particles()
+        assert np.array_equal(got, want)
+    assert oracle.stats(parts, size)["max_neighbours"] >= 6
+    info = sim.info()
+    assert info["engine"] == pkg.ENGINE_KSTEP and info["engine_switches"] == 0
+    sim.close()
+
+
+def test_kstep_hands_over_when_a_clump_exceeds_its_lists(pkg, oracle):
+    """More in-range neighbours per particle than the kstep kernel's force word / canonical-path scratch hold (a 40-particle
+    clump half a cutoff wide): the launch reports the overflow, leaves its input intact, and the handle finishes the batch on the
+    cellsort engine (which has no capacities) -- still bit-identical to the oracle."""
+    rng = np.random.default_rng(3)
+    size = box_size(4000)
+    n = 40
+    parts = np.zeros((n + 50, 6))
+    parts[:n, 0] = 0.7 + 0.005 * rng.random(n)
+    parts[:n, 1] = 0.7 + 0.005 * rng.random(n)
+    parts[n:, 0] = 0.1 + 1.2 * rng.random(50)
+    parts[n:, 1] = 0.1 + 1.2 * rng.random(50)
+    want = parts.copy()
+    sim = pkg.Simulation(parts, len(parts), size, engine=pkg.ENGINE_KSTEP, tile_cells=64)
+    assert sim.info()["engine"] == pkg.ENGINE_KSTEP
+    oracle.step(want, size, 3)
+    got = sim.step(3).sync().read_particles()
+    info = sim.info()
+    assert info["engine"] == pkg.ENGINE_CELLSORT and info["engine_switches"] == 1
+    assert rel_err(got, want) <= 1e-12
+    sim.close()
+
+
 def test_empty_and_dense_inputs(pkg, oracle):
     sim = pkg.Simulation(np.zeros((0, 6)), 0, 0.5)
     sim.step(3).sync()
