@@ -39,18 +39,21 @@
 //            that tile no longer needs, velocities into a landing zone that aliases the (then dead) cell table -- so the
 //            copies fly during the store phase, from which the loader warp is excused (named barrier of the other warps)
 //   arrive   velocities leave the landing zone, the halo is ring-sorted, own ids are parked, the cell table is wiped
-//   bin      every loaded particle into a (TS+2H+2)^2 cell table in shared memory: per cell the head of a linked list
+//   bin      every loaded particle into a (TS+2H+4)^2 cell table (tile + halo + two empty guard rings) in shared memory: per cell the head of a linked list
 //            (reference part3/gpu.cu:92-112 does this in global memory with 16 fixed slots) + one occupancy bit
-//   K times  pass 1  each particle takes the 9 occupancy bits of its 3x3 neighbourhood (reference serial.cpp:102-117),
-//                    walks the non-empty cells, tests candidates in exact FP64 and remembers up to two in-range
-//                    neighbours; in-range pairs go to a per-WARP list
-//            eval    the warp evaluates its listed pairs densely, one lane per pair (sqrt + divisions of
-//                    reference serial.cpp:29-33 run once per warp and sub-step instead of once per particle pass)
-//            pass 2  sum (<= 2 terms are order independent; >= 3 take the canonical-order exact path), move + reflect
-//                    (serial.cpp:46-61), speed check, new cell, insert into the cell table of the NEXT sub-step
-//            one __syncthreads per sub-step: positions, list links and occupancy maps are double buffered by sub-step
-//            parity, the two parities of a cell's list head share one 32-bit word (halves), entries carry the
-//            sub-step number so a table is wiped once per tile only
+//   search   ONCE per tile: every particle walks the earlier half of its 5x5 cell neighbourhood (so each unordered pair is met
+//            once) and lists the pairs within rs = cutoff + the distance two particles can close in the remaining sub-steps
+//            (the speed bound is enforced below): the tile's candidate-pair list, ~1.25 pairs per particle.  Pairs that are
+//            within the cutoff right now are handed to the first sub-step directly.  The cell table is not touched again.
+//   K times  check   (sub-steps 2..K) the listed pairs are re-tested in exact FP64 against the cutoff (reference
+//                    serial.cpp:24-26), one lane per pair; the in-range ones are collected tile-wide
+//            eval    the in-range pairs are evaluated densely, one lane per pair, full warps: the sqrt + divisions of
+//                    reference serial.cpp:29-33 run once per PAIR (the second particle takes the exact negative); the
+//                    reference's 3x3 cell structure (serial.cpp:102-117) is re-imposed exactly here.  Each particle's
+//                    force word counts its in-range neighbours and remembers its first two pairs
+//            move    sum (<= 2 terms are order independent; >= 3 take the canonical-order exact path), move + reflect
+//                    (serial.cpp:46-61), speed check; after the last sub-step: final cell -> class
+//            positions are double buffered by sub-step parity
 //   store    particles whose final cell lies in the tile are ranked inside their class (shared atomics), the class
 //            offsets become the tile's new header, and pos / vel / id (/ acc) are stored to the other parity.  Tiles
 //            of a slab's first / last row also store their facing band straight into the neighbour GPU's ghost row.
