@@ -213,6 +213,7 @@ void kstep_destroy(psim_sim* sim);
 long long kstep_bytes(psim_sim* sim);
 void kstep_info(psim_sim* sim, psim_info_t* out);
 int kstep_default_tile(int bincnt);
+bool kstep_tile_supported(int ts);   // 16, 32, 64 and one build-time tunable size (psim_kstep.cu)
 int kstep_exchange(psim_sim* sim, int parity, cudaStream_t s);  // psim_comm.cpp
 void kstep_shared_buffers(psim_sim* sim, char** parity0, char** parity1, size_t* bytes, int* ntx);
 void kstep_row_ranges(psim_sim* sim, int parity, int lrow, char* ptr[4], size_t bytes[4]);

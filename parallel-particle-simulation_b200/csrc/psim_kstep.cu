@@ -87,6 +87,17 @@ template <> struct KCfg<32, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T
 #endif
 template <> struct KCfg<64, 3> { static constexpr int KMAX = 2, T = PSIM_KSTEP_T64, CTAS = 2, CAP = 1024, NMAX = 1216; };
 template <> struct KCfg<64, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T64, CTAS = 2, CAP = 1024, NMAX = 1280; };
+// one more tile size (halo 4 only), tunable at build time: the per-sub-step passes run in rounds of T particles, so the
+// tile size decides how full the last round is (54-cell tiles: ~720 / 673 / 627 processed particles = two rounds of 384)
+#ifndef PSIM_KSTEP_TSX
+#define PSIM_KSTEP_TSX 54
+#define PSIM_KSTEP_TX 384
+#define PSIM_KSTEP_CX 2
+#define PSIM_KSTEP_CAPX 768
+#define PSIM_KSTEP_NMAXX 960
+#endif
+constexpr int kTSX = PSIM_KSTEP_TSX;
+template <> struct KCfg<kTSX, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_TX, CTAS = PSIM_KSTEP_CX, CAP = PSIM_KSTEP_CAPX, NMAX = PSIM_KSTEP_NMAXX; };
 
 constexpr int kHdrInts = 16;          // per tile: ten prefix offsets (ring order TL T TR R BR B BL L M, [9] = population)
 constexpr int kRanges = 10;           // slot ranges that make up a tile's region
@@ -144,6 +155,7 @@ template <int TS, int H> struct __align__(16) KSmem {
 
 static_assert(2 * (sizeof(KSmem<64, 4>) + 1024) <= 233472 && 2 * (sizeof(KSmem<64, 3>) + 1024) <= 233472,
               "two CTAs of the 64-cell kernel must fit one SM's shared memory");
+static_assert(KCfg<kTSX, 4>::CTAS * (sizeof(KSmem<kTSX, 4>) + 1024) <= 233472, "the CTAs of the extra tile size must fit one SM's shared memory");
 
 // the ten ranges: neighbour (dr, dc) and the classes [cb, ce) of ITS stripe that lie within H cells of this tile
 __constant__ signed char kRangeTab[kRanges][4] = {
@@ -1191,6 +1203,7 @@ static int klaunch_rows(psim_sim* sim, KstepEngine* e, int parity_in, int nsub, 
         case 32 * 8 + 4: return klaunch<32, 4>(sim, e, P, store_acc, s);
         case 64 * 8 + 3: return klaunch<64, 3>(sim, e, P, store_acc, s);
         case 64 * 8 + 4: return klaunch<64, 4>(sim, e, P, store_acc, s);
+        case kTSX * 8 + 4: return klaunch<kTSX, 4>(sim, e, P, store_acc, s);
     }
     return fail(PSIM_ERR_INVALID, "kstep tile size %d / halo %d not instantiated", e->ts, e->h);
 }
@@ -1222,6 +1235,8 @@ static int kconfigure(KstepEngine* e) {
     return PSIM_OK;
 }
 
+bool kstep_tile_supported(int ts) { return ts == 16 || ts == 32 || ts == 64 || ts == kTSX; }
+
 int kstep_default_tile(int bincnt) {
     // 64-cell tiles amortise the halo best (region / tile = 1.34); smaller boxes take smaller tiles so that there are
     // enough tiles to spread over the SMs
@@ -1248,7 +1263,7 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     };
     int ts = cfg->tile_cells;
     if (ts == 0) ts = kstep_default_tile(sim->bincnt);
-    if (ts != 16 && ts != 32 && ts != 64) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32 or 64 (got %d)", ts);
+    if (!kstep_tile_supported(ts)) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32, %d or 64 (got %d)", kTSX, ts);
     auto* e = new KstepEngine();
     sim->kstep = e;
     e->ts = ts;
@@ -1259,6 +1274,10 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     if (ts == 16) PSIM_TRY(halo == 3 ? (kconfigure<16, 3>(e)) : (kconfigure<16, 4>(e)));
     if (ts == 32) PSIM_TRY(halo == 3 ? (kconfigure<32, 3>(e)) : (kconfigure<32, 4>(e)));
     if (ts == 64) PSIM_TRY(halo == 3 ? (kconfigure<64, 3>(e)) : (kconfigure<64, 4>(e)));
+    if (ts == kTSX) {
+        if (halo != 4) return fail(PSIM_ERR_INVALID, "%d-cell tiles come with a 4-cell halo only", kTSX);
+        PSIM_TRY((kconfigure<kTSX, 4>(e)));
+    }
     e->grid_cap = e->sms * e->ctas_per_sm;
     e->ksteps = e->kmax;
     if (const char* r = std::getenv("PSIM_RINGSORT")) e->ringsort = std::atoi(r) != 0;
@@ -1299,27 +1318,53 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
         e->parity = 0;
         return PSIM_OK;
     }
-    // fill: device input is read in place; host input is streamed through a bounded staging buffer
-    {
-        DeviceArena stage;
-        particle_t* d_stage = nullptr;
-        const int chunk = parts_on_device ? n : std::min(n, 4 << 20);
-        if (!parts_on_device && n > 0) PSIM_TRY(stage.alloc(&d_stage, (size_t)chunk));
-        for (int off = 0; off < n; off += chunk) {
-            const int m = std::min(chunk, n - off);
-            const particle_t* src = parts + off;
-            if (!parts_on_device) {
-                PSIM_CUDA(cudaMemcpyAsync(d_stage, parts + off, sizeof(particle_t) * (size_t)m, cudaMemcpyHostToDevice, s));
-                src = d_stage;
-            }
-            kstep_fill_kernel<<<(m + 255) / 256, 256, 0, s>>>(src, m, off, sim->bincnt, ts, e->cap, e->ntx, e->tr_begin, e->tr_end,
-                                                              e->tr_begin - 1, e->pos[0], e->vel[0], e->sid[0], e->tcount,
-                                                              sim->d_err);
+    // fill: device input is read in place; host input is streamed through two bounded staging buffers on two auxiliary
+    // streams, so that the scatter of chunk k runs while chunk k + 1 is on the wire (the copies of both streams share the one
+    // host->device engine; stream order protects each staging buffer)
+    if (parts_on_device) {
+        if (n > 0) {
+            kstep_fill_kernel<<<(n + 255) / 256, 256, 0, s>>>(parts, n, 0, sim->bincnt, ts, e->cap, e->ntx, e->tr_begin, e->tr_end,
+                                                              e->tr_begin - 1, e->pos[0], e->vel[0], e->sid[0], e->tcount, sim->d_err);
             ++sim->launches;
         }
         PSIM_CUDA(cudaGetLastError());
-        if (!parts_on_device) PSIM_CUDA(cudaStreamSynchronize(s));   // the staging buffer is freed below
+    } else if (n > 0) {
+        DeviceArena stage;
+        particle_t* d_stage[2] = {nullptr, nullptr};
+        cudaStream_t aux[2] = {nullptr, nullptr};
+        cudaEvent_t ev = nullptr;
+        const int chunk = std::min(n, 2 << 20);
+        const int nbuf = n > chunk ? 2 : 1;
+        int st = PSIM_OK;
+        cudaError_t ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        for (int b = 0; b < nbuf && st == PSIM_OK && ce == cudaSuccess; ++b) {
+            st = stage.alloc(&d_stage[b], (size_t)chunk);
+            if (st == PSIM_OK) ce = cudaStreamCreateWithFlags(&aux[b], cudaStreamNonBlocking);
+        }
+        if (st == PSIM_OK && ce == cudaSuccess) ce = cudaEventRecord(ev, s);   // the zeroed tile counters
+        for (int b = 0; b < nbuf && st == PSIM_OK && ce == cudaSuccess; ++b) ce = cudaStreamWaitEvent(aux[b], ev, 0);
+        int k = 0;
+        for (int off = 0; off < n && st == PSIM_OK && ce == cudaSuccess; off += chunk, ++k) {
+            const int m = std::min(chunk, n - off), b = k % nbuf;
+            ce = cudaMemcpyAsync(d_stage[b], parts + off, sizeof(particle_t) * (size_t)m, cudaMemcpyHostToDevice, aux[b]);
+            if (ce != cudaSuccess) break;
+            kstep_fill_kernel<<<(m + 255) / 256, 256, 0, aux[b]>>>(d_stage[b], m, off, sim->bincnt, ts, e->cap, e->ntx, e->tr_begin, e->tr_end,
+                                                                   e->tr_begin - 1, e->pos[0], e->vel[0], e->sid[0], e->tcount, sim->d_err);
+            ++sim->launches;
+            ce = cudaGetLastError();
+        }
+        for (int b = 0; b < nbuf; ++b) {   // everything below is ordered behind both auxiliary streams; the staging is freed after them
+            if (!aux[b]) continue;
+            if (ce == cudaSuccess) ce = cudaEventRecord(ev, aux[b]);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, ev, 0);
+            const cudaError_t ce2 = cudaStreamSynchronize(aux[b]);
+            if (ce == cudaSuccess) ce = ce2;
+            cudaStreamDestroy(aux[b]);
+        }
+        if (ev) cudaEventDestroy(ev);
         stage.release();
+        PSIM_TRY(st);
+        if (ce != cudaSuccess) return fail(PSIM_ERR_CUDA, "kstep_create: upload: %s", cudaGetErrorString(ce));
     }
     lap("upload + fill");
     return kstep_finish_fill(sim, unsuitable);

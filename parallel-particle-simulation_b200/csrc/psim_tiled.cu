@@ -1560,7 +1560,7 @@ extern "C" int psim_slab_rows(int bin_count, int tile_cells, int rank, int nrank
     if (bin_count < 1 || nranks < 1 || rank < 0 || rank >= nranks || !row_begin || !row_end)
         return fail(PSIM_ERR_INVALID, "psim_slab_rows: bad argument");
     const int ts = tile_cells ? tile_cells : kstep_default_tile(bin_count);   // 0: what the default (kstep) engine picks for this box
-    if (ts != 16 && ts != 32 && ts != 64) return fail(PSIM_ERR_INVALID, "tile_cells must be 16, 32 or 64 (got %d)", ts);
+    if (!kstep_tile_supported(ts)) return fail(PSIM_ERR_INVALID, "tile_cells %d is not a tile size of this build", ts);
     const int ntx = tiled_tile_rows(bin_count, ts);
     if (nranks > ntx) return fail(PSIM_ERR_INVALID, "more slabs (%d) than tile rows (%d)", nranks, ntx);
     int b, e;
