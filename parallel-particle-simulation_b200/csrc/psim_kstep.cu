@@ -82,19 +82,22 @@ template <> struct KCfg<16, 4> { static constexpr int KMAX = 3, T = 64,  CTAS = 
 #endif
 template <> struct KCfg<32, 3> { static constexpr int KMAX = 2, T = PSIM_KSTEP_T32, CTAS = PSIM_KSTEP_C32, CAP = 352,  NMAX = 480; };
 template <> struct KCfg<32, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T32, CTAS = PSIM_KSTEP_C32, CAP = 352,  NMAX = 512; };
+// 64-cell tiles: three CTAs of 256 threads per SM (one CTA's shared memory is 72 KB).  A tile's phases are separated by
+// barriers and contain serial stretches (the exact sqrt / division chain of the pair evaluation); what fills those gaps
+// is the other CTAs of the SM -- measured: 1 CTA 17.2, 2 CTAs 31.2 G particle-steps/s at 256 threads (profiles/README.md)
 #ifndef PSIM_KSTEP_T64
-#define PSIM_KSTEP_T64 384
+#define PSIM_KSTEP_T64 256
+#define PSIM_KSTEP_C64 3
 #endif
-template <> struct KCfg<64, 3> { static constexpr int KMAX = 2, T = PSIM_KSTEP_T64, CTAS = 2, CAP = 1024, NMAX = 1216; };
-template <> struct KCfg<64, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T64, CTAS = 2, CAP = 1024, NMAX = 1280; };
-// one more tile size (halo 4 only), tunable at build time: the per-sub-step passes run in rounds of T particles, so the
-// tile size decides how full the last round is (54-cell tiles: ~720 / 673 / 627 processed particles = two rounds of 384)
+template <> struct KCfg<64, 3> { static constexpr int KMAX = 2, T = PSIM_KSTEP_T64, CTAS = PSIM_KSTEP_C64, CAP = 1024, NMAX = 1216; };
+template <> struct KCfg<64, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_T64, CTAS = PSIM_KSTEP_C64, CAP = 1024, NMAX = 1280; };
+// one more tile size (halo 4 only), tunable at build time (tile-size sweeps: profiles/README.md)
 #ifndef PSIM_KSTEP_TSX
-#define PSIM_KSTEP_TSX 54
-#define PSIM_KSTEP_TX 384
-#define PSIM_KSTEP_CX 2
-#define PSIM_KSTEP_CAPX 768
-#define PSIM_KSTEP_NMAXX 960
+#define PSIM_KSTEP_TSX 48
+#define PSIM_KSTEP_TX 192
+#define PSIM_KSTEP_CX 4
+#define PSIM_KSTEP_CAPX 640
+#define PSIM_KSTEP_NMAXX 800
 #endif
 constexpr int kTSX = PSIM_KSTEP_TSX;
 template <> struct KCfg<kTSX, 4> { static constexpr int KMAX = 3, T = PSIM_KSTEP_TX, CTAS = PSIM_KSTEP_CX, CAP = PSIM_KSTEP_CAPX, NMAX = PSIM_KSTEP_NMAXX; };
@@ -104,6 +107,7 @@ constexpr int kRanges = 10;           // slot ranges that make up a tile's regio
 constexpr unsigned kNoOwner = 0xFFFFu;
 constexpr int kGuard = 2;             // empty guard rings around the cell table: the candidate search looks two cells out
 constexpr int kSlowMax = 16;          // in-range neighbours the canonical-order path sorts (beyond: hand-over to cellsort)
+constexpr int kSlowSlots = 32;        // particles of one tile and sub-step that take the canonical-order path (beyond: hand-over)
 // per-particle force word: count << 28 | second reference << 14 | first reference; a reference is the slot of an
 // evaluated pair (13 bits) plus one bit that says "I am the pair's second particle: negate"
 constexpr unsigned kRefBits = 14, kRefMask = (1u << kRefBits) - 1u, kRefNeg = 1u << 13, kCntShift = 28;
@@ -116,45 +120,57 @@ template <int TS, int H> struct KDims {
     static constexpr int BM = (TW * RW + 3) / 4 * 4;           // the occupancy map, padded to 16 bytes
     static constexpr int NW = C::T / 32;
     static constexpr int PCAP = 2 * C::NMAX;                   // candidate pairs of one region (expected 1.25 per particle)
-    static constexpr int NCON = C::NMAX / 2;                   // in-range pairs of one sub-step (expected 0.1 per particle)
+    static constexpr int NCON = C::NMAX / 2;                   // in-range pairs of one sub-step (expected 0.05 per particle)
+    static constexpr int HREG = 2, HMAX = HREG * C::T;         // halo particles the ring sort handles (HREG per thread, in registers)
     static_assert(TS >= 2 * H && C::KMAX < H && C::NMAX < 0xFFF && C::T % 32 == 0 && C::CAP <= 0xFFF, "configuration");
     static_assert(TW <= 255, "cell codes pack row and column into 8 bits each");
     static_assert(NCON < (int)kRefNeg, "pair references are 13 bits");
+    static constexpr int NLIST = NCON - kSlowSlots;            // ... of which the last kSlowSlots result slots serve the canonical-order path
+    static_assert(PCAP >= 2 * NCON && NLIST > 32, "the first sub-step's in-range pairs grow down from the end of the candidate list");
 };
 
 template <int TS, int H> struct __align__(16) KSmem {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
-    struct Tables {   // everything the candidate search needs; dead once the last sub-step has evaluated its pairs
+    struct Tables {   // the cell table: everything the candidate search needs; dead once the search is over
         alignas(16) unsigned short head[D::NC8];   // per cell: first particle of its list (slot + 1, 0 = empty)
         alignas(16) unsigned bitmap[D::BM];        // one occupancy bit per cell
         alignas(16) unsigned short next[C::NMAX];  // list links (slot + 1, 0 = end)
-        alignas(16) unsigned pairs[D::PCAP];       // candidate pairs i | j << 16: every pair that can come within the cutoff during this launch
     };
-    double2 pos[2][C::NMAX];                 // positions, double buffered by sub-step (TMA destination: the buffer the previous tile left free)
-    double2 vel[C::NMAX];                    // velocities (only the owner lane of a particle touches them during the sub-steps)
-    double2 wres[D::NCON];                   // contribution of evaluated pair g to its first particle (the second one takes the negative)
+    struct Force {    // alive from the end of the search to the end of the last sub-step: shares the cell table's storage
+        double2 wres[D::NCON];                     // contribution of evaluated pair g to its first particle (the second one takes the negative)
+        unsigned inlist[D::NCON];                  // the in-range pairs of the current sub-step, waiting for their dense evaluation
+    };
+    struct Work {
+        union alignas(16) {
+            Tables t;
+            Force f;
+        } a;
+        alignas(16) unsigned pairs[D::PCAP];       // candidate pairs i | j << 16 (from the front); the pairs already in range at the first
+    };                                             // sub-step are listed a second time from the back (the search cannot use `inlist` yet)
+    double2 pos[C::NMAX];                    // positions, updated in place (a sub-step's phases are separated by barriers)
+    double2 vel[C::NMAX];                    // velocities in LOAD order (TMA destination): a ring-sorted halo particle finds its own through horig
     union alignas(16) {
-        Tables t;
-        double2 vland[C::NMAX];              // landing zone of the NEXT tile's velocities while this tile is stored (TMA destination)
+        Work w;
+        double2 pland[C::NMAX];              // landing zone of the NEXT tile's positions while this tile is stored (TMA destination)
     } u;
     unsigned pw[C::NMAX];                    // bin -> search: table row << 8 | column;  sub-steps: force word;  store phase: class << 12 | rank
-    unsigned inlist[D::NCON];                // the in-range pairs of the current sub-step, waiting for their dense evaluation
     unsigned short wslow[D::NW][kSlowMax];   // per warp: neighbours of a particle on the canonical-order path (rank << 12 | slot)
-    int id[C::CAP];                          // ids of the tile's own stripe (halo particles that end up inside fetch theirs at store time)
-    unsigned short horig[C::T];              // halo particle -> its shared slot before the ring sort (id look-up at store time)
-    unsigned long long mbar;                 // TMA completion
+    unsigned short horig[D::HMAX];           // ring-sorted halo particle -> its slot in load order (velocity, id look-up at store time)
+    unsigned long long mbar_p, mbar_v;       // TMA completion: positions of the next tile, velocities of this one
     int rsrc[2][kRanges], rlen[2][kRanges], rdst[2][kRanges];   // slot ranges of this tile / the next: global slot, length, first shared slot
     int ncount[2];                           // particles of this tile's / the next tile's region
     int nproc[8];                            // per sub-step: particles that are still processed (own + rings that still matter)
     int ringcnt[8];
     int segcnt[12], segoff[12];
     int npairs, ncon, work;
+    int nslow[2], nslowslot[2];              // by sub-step parity: particles with >= 3 in-range neighbours, result slots handed out
     int flags, hw_region, hw_stripe, hw_pairs;
 };
 
-static_assert(2 * (sizeof(KSmem<64, 4>) + 1024) <= 233472 && 2 * (sizeof(KSmem<64, 3>) + 1024) <= 233472,
-              "two CTAs of the 64-cell kernel must fit one SM's shared memory");
+static_assert(KCfg<64, 4>::CTAS * (sizeof(KSmem<64, 4>) + 1024) <= 233472 && KCfg<64, 3>::CTAS * (sizeof(KSmem<64, 3>) + 1024) <= 233472,
+              "the CTAs of the 64-cell kernel must fit one SM's shared memory");
+static_assert(sizeof(KSmem<64, 4>::Force) <= sizeof(KSmem<64, 4>::Tables), "the force lists of a 64-cell tile fit inside its cell table");
 static_assert(KCfg<kTSX, 4>::CTAS * (sizeof(KSmem<kTSX, 4>) + 1024) <= 233472, "the CTAs of the extra tile size must fit one SM's shared memory");
 
 // the ten ranges: neighbour (dr, dc) and the classes [cb, ce) of ITS stripe that lie within H cells of this tile
@@ -252,7 +268,7 @@ template <int TS, int H>
 __device__ __forceinline__ void k_bin_particle(KSmem<TS, H>& S, int p, int lr, int lc) {
     constexpr int TW = KDims<TS, H>::TW, RW = KDims<TS, H>::RW;
     const int cell = lr * TW + lc;
-    unsigned* w = reinterpret_cast<unsigned*>(S.u.t.head) + (cell >> 1);
+    unsigned* w = reinterpret_cast<unsigned*>(S.u.w.a.t.head) + (cell >> 1);
     const unsigned sh = (unsigned)(cell & 1) << 4;
     const unsigned ent = (unsigned)(p + 1) << sh, keep = ~(0xFFFFu << sh);
     unsigned old = *w;
@@ -261,9 +277,9 @@ __device__ __forceinline__ void k_bin_particle(KSmem<TS, H>& S, int p, int lr, i
         if (prev == old) break;
         old = prev;
     }
-    S.u.t.next[p] = (unsigned short)((old >> sh) & 0xFFFFu);
+    S.u.w.a.t.next[p] = (unsigned short)((old >> sh) & 0xFFFFu);
     S.pw[p] = (unsigned)((lr << 8) | lc);
-    atomicOr(&S.u.t.bitmap[lr * RW + (lc >> 5)], 1u << (lc & 31));
+    atomicOr(&S.u.w.a.t.bitmap[lr * RW + (lc >> 5)], 1u << (lc & 31));
 }
 // final cell -> owner test, class, rank inside the class
 template <int TS, int H>
@@ -292,17 +308,17 @@ __device__ __forceinline__ void k_classify(KSmem<TS, H>& S, int p, int lr, int l
 }
 
 // Walls (reference serial.cpp:53-61), out of line and through shared memory: only tiles whose region touches a wall get here,
-// and keeping the bounce loops out of pass 2 keeps their registers out of it too.
+// and keeping the bounce loops out of the move phase keeps their registers out of it too.
 // (Out-of-line functions name the shared-memory block themselves instead of taking pointers into it: a generic pointer to
 // shared memory makes the compiler rebuild the CTA's shared window address -- S2R SR_CgaCtaId -- all over the hot loops.)
 template <int TS, int H>
-static __device__ __noinline__ void k_reflect_in_place(int bn, int p, double size) {
+static __device__ __noinline__ void k_reflect_in_place(int p, int vi, double size) {
     extern __shared__ __align__(128) unsigned char k_smem_raw[];
     KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
-    double2 q = S.pos[bn][p], v = S.vel[p];
+    double2 q = S.pos[p], v = S.vel[vi];
     reflect_particle(q.x, q.y, v.x, v.y, size);
-    S.pos[bn][p] = q;
-    S.vel[p] = v;
+    S.pos[p] = q;
+    S.vel[vi] = v;
 }
 
 // Are the cells of two particles the same or adjacent (the reference only ever compares a particle with the members of its
@@ -320,14 +336,16 @@ __device__ __forceinline__ int k_neighbour_rank(const double2 a, const double2 c
 // and lists the pairs within rs (cutoff + twice the distance a particle may travel in the remaining sub-steps of this launch,
 // which the speed check enforces): no other pair can come within the cutoff before the next launch.  The reference's 3x3
 // walk (serial.cpp:102-117) is the rs = cutoff special case; its cell structure is re-imposed exactly when a pair is evaluated.
+// Pairs that are within the cutoff right now are listed a second time, from the END of the candidate array downwards: the first
+// sub-step evaluates them without a check pass (`inlist` shares its storage with the cell table the search is still reading).
 template <int TS, int H>
-static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int b, int n, int np0, double rs2) {
+static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int n, int np0, double rs2) {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
     constexpr int TW = D::TW, RW = D::RW;
     const int lane = threadIdx.x & 31;
-    const double2* posb = S.pos[b];
-    const unsigned short* next = S.u.t.next;
+    const double2* posb = S.pos;
+    const unsigned short* next = S.u.w.a.t.next;
     const int nch = (n + 31) >> 5;
     // chunks of 32 particles are handed out dynamically (their cost varies with the local density); the warp reconverges
     // after every chunk -- without the explicit __syncwarp the lanes drift apart and every later instruction is issued
@@ -345,13 +363,13 @@ static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int b, int n, i
         const int lr = (int)(cc >> 8), lc = (int)(cc & 0xFFu);
         const double2 me = posb[p];
         // occupancy of rows lr-2, lr-1 (five cells from column lc-2) and of row lr (columns lc-2, lc-1, and my own cell)
-        const unsigned* rb = S.u.t.bitmap + (lr - 2) * RW + ((lc - 2) >> 5);
+        const unsigned* rb = S.u.w.a.t.bitmap + (lr - 2) * RW + ((lc - 2) >> 5);
         const unsigned sh = (unsigned)(lc - 2) & 31u;
         unsigned m = (__funnelshift_r(rb[0], rb[1], sh) & 31u) | ((__funnelshift_r(rb[RW], rb[RW + 1], sh) & 31u) << 8) |
                      ((__funnelshift_r(rb[2 * RW], rb[2 * RW + 1], sh) & 3u) << 16);
         const unsigned own_next = next[p];
         if (own_next) m |= 1u << 18;   // members of my own cell that follow me in its list
-        const unsigned short* hcorner = S.u.t.head + (lr - 2) * TW + (lc - 2);
+        const unsigned short* hcorner = S.u.w.a.t.head + (lr - 2) * TW + (lc - 2);
 #pragma unroll 1
         while (m) {
             const int k = __ffs((int)m) - 1;
@@ -367,10 +385,10 @@ static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int b, int n, i
                 if (r2 <= rs2 && min((unsigned)p, j) < (unsigned)np0) {
                     const unsigned ij = (unsigned)p | (j << 16);
                     const int slot = k_atoms_add(&S.npairs, 1);
-                    if (slot < D::PCAP) S.u.t.pairs[slot] = ij;
+                    if (slot < D::PCAP) S.u.w.pairs[slot] = ij;
                     if (!(r2 > kCutoff2) && r2 != 0.0) {   // in range right now: the first sub-step evaluates it
                         const int g = k_atoms_add(&S.ncon, 1);
-                        if (g < D::NCON) S.inlist[g] = ij;
+                        if (g < D::NLIST) S.u.w.pairs[D::PCAP - 1 - g] = ij;
                     }
                 }
             } while (h);
@@ -386,7 +404,7 @@ static __device__ __forceinline__ void k_search(KSmem<TS, H>& S, int b, int n, i
 // serial.cpp:29-33 run once per PAIR (the second particle takes the exact negative).  Each particle's force word counts its
 // in-range neighbours and remembers the first two evaluated pairs.
 template <int TS, int H>
-static __device__ __forceinline__ void k_pair_check(KSmem<TS, H>& S, int b, int np, int nvalid) {
+static __device__ __forceinline__ void k_pair_check(KSmem<TS, H>& S, int np, int nvalid) {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
     constexpr int T = C::T;
@@ -399,9 +417,9 @@ static __device__ __forceinline__ void k_pair_check(KSmem<TS, H>& S, int b, int 
         bool hit = false;
         unsigned ij = 0;
         if (e < npairs) {
-            ij = S.u.t.pairs[e];
+            ij = S.u.w.pairs[e];
             const unsigned i = ij & 0xFFFFu, j = ij >> 16;
-            const double2 a = S.pos[b][i], c = S.pos[b][j];
+            const double2 a = S.pos[i], c = S.pos[j];
             const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
             const double r2 = pair_r2(dx, dy);
             // a pair matters while one of the two is still processed and both still carry valid positions; pairs at
@@ -414,20 +432,21 @@ static __device__ __forceinline__ void k_pair_check(KSmem<TS, H>& S, int b, int 
             if (lane == 0) gbase = atomicAdd(&S.ncon, __popc(bal));
             gbase = __shfl_sync(0xffffffffu, gbase, 0);
             const int g = gbase + __popc(bal & lt_mask);
-            if (hit && g < D::NCON) S.inlist[g] = ij;
+            if (hit && g < D::NLIST) S.u.w.a.f.inlist[g] = ij;
         }
     }
 }
 
+// `list` / `dir`: the in-range pairs -- inlist upwards, or (first sub-step) the tail of the candidate array downwards
 template <int TS, int H>
-static __device__ __forceinline__ void k_pair_eval(KSmem<TS, H>& S, int b, int np, int bincnt) {
+static __device__ __forceinline__ void k_pair_eval(KSmem<TS, H>& S, const unsigned* list, int dir, int np, int bincnt, int sidx) {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
-    const double2* posb = S.pos[b];
-    const int ncon = min(S.ncon, D::NCON);
+    const double2* posb = S.pos;
+    const int ncon = min(S.ncon, D::NLIST);
 #pragma unroll 1
     for (int g = threadIdx.x; g < ncon; g += C::T) {
-        const unsigned ij = S.inlist[g];
+        const unsigned ij = list[dir * g];
         const unsigned i = ij & 0xFFFFu, j = ij >> 16;
         const double2 a = posb[i], c = posb[j];
         const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
@@ -438,7 +457,7 @@ static __device__ __forceinline__ void k_pair_eval(KSmem<TS, H>& S, int b, int n
         if (adjacent) {
             double cx, cy;
             pair_contrib(dx, dy, pair_r2(dx, dy), cx, cy);
-            S.wres[g] = make_double2(cx, cy);
+            S.u.w.a.f.wres[g] = make_double2(cx, cy);
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 const unsigned q = side ? j : i;
@@ -446,6 +465,7 @@ static __device__ __forceinline__ void k_pair_eval(KSmem<TS, H>& S, int b, int n
                     const unsigned cnt = atomicAdd(&S.pw[q], 1u << kCntShift) >> kCntShift;
                     const unsigned ref = (unsigned)g | (side ? kRefNeg : 0u);
                     if (cnt < 2u) atomicOr(&S.pw[q], ref << (cnt * kRefBits));
+                    if (cnt == 2u) atomicAdd(&S.nslow[sidx], 1);            // a third neighbour: the canonical-order pass must run
                     if (cnt >= 14u) atomicOr(&S.flags, kErrSmemOverflow);   // the 4-bit count would wrap: hand over
                 }
             }
@@ -486,14 +506,14 @@ static __device__ __forceinline__ double2 kslow_sum(const double2* xy, unsigned 
 }
 
 template <int TS, int H>
-static __device__ __noinline__ double2 kslow_force(int b, unsigned slow, int p, int nvalid, int bincnt) {
+static __device__ __noinline__ double2 kslow_force(unsigned slow, int p, int nvalid, int bincnt) {
     using D = KDims<TS, H>;
     extern __shared__ __align__(128) unsigned char k_smem_raw[];
     KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const double2* xy = S.pos[b];
-    const int npairs = min(S.npairs, D::PCAP);
+    const double2* xy = S.pos;
+    const int npairs = min(S.npairs, D::PCAP);   // (the first sub-step's list at the tail never overlaps: checked after the search)
     double2 out = make_double2(0.0, 0.0);
     while (slow) {
         const int leader = __ffs((int)slow) - 1;
@@ -506,7 +526,7 @@ static __device__ __noinline__ double2 kslow_force(int b, unsigned slow, int p, 
             bool hit = false;
             unsigned ent = 0;
             if (e < npairs) {
-                const unsigned ij = S.u.t.pairs[e];
+                const unsigned ij = S.u.w.pairs[e];
                 const unsigned a = ij & 0xFFFFu, c = ij >> 16;
                 if ((a == i || c == i) && max(a, c) < (unsigned)nvalid) {
                     const unsigned o = a == i ? c : a;
@@ -535,16 +555,48 @@ static __device__ __noinline__ double2 kslow_force(int b, unsigned slow, int p, 
     return out;
 }
 
+// ---- canonical-order pass (only in sub-steps where some particle has three or more in-range neighbours) -------------------------
+// Runs between the pair evaluation and the move phase, i.e. while every position is still the sub-step's input (the move phase
+// updates positions in place).  The sum lands in one of the last kSlowSlots result slots and the particle's force word is rewritten
+// to "one neighbour, that slot": +0 + sum == sum exactly (a sum that starts from +0 is never -0).
+template <int TS, int H>
+static __device__ __noinline__ void k_slow_phase(int np, int nvalid, int bincnt, int sidx) {
+    using D = KDims<TS, H>;
+    extern __shared__ __align__(128) unsigned char k_smem_raw[];
+    KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nch = (np + 31) >> 5;
+    for (int ch = warp; ch < nch; ch += D::NW) {
+        const int p = ch * 32 + lane;
+        const unsigned cnt = (p < np ? S.pw[p] : 0u) >> kCntShift;
+        const unsigned slow = __ballot_sync(0xffffffffu, cnt >= 3u);
+        if (!slow) continue;
+        const double2 a = kslow_force<TS, H>(slow, p, nvalid, bincnt);
+        if (cnt >= 3u) {
+            const int k = atomicAdd(&S.nslowslot[sidx], 1);
+            if (k < kSlowSlots) {
+                const int slot = D::NCON - 1 - k;
+                S.u.w.a.f.wres[slot] = a;
+                S.pw[p] = (1u << kCntShift) | (unsigned)slot;
+            } else {
+                atomicOr(&S.flags, kErrSmemOverflow);   // hand over
+                S.pw[p] = 0u;
+            }
+        }
+    }
+}
+
 // ---- a sub-step, second half: sum, move, speed check; after the last one: final cell -> class ---------------------------------
+// Positions are updated in place (only the owner lane of a particle touches them here; the check / evaluation phases that read
+// other particles' positions are separated from this one by barriers).  A ring-sorted halo particle finds its velocity, which
+// stays in load order, through horig.
 template <int TS, int H, bool kStoreAcc>
-static __device__ __forceinline__ void k_move_phase(KSmem<TS, H>& S, int b, int np, int nvalid, bool last, int rbase, int cbase, bool at_wall,
-                                                    int bincnt, double size, double vlim2, double2* acc_tmp) {
+static __device__ __forceinline__ void k_move_phase(KSmem<TS, H>& S, int np, int n_own, bool sorted, bool last, int rbase, int cbase,
+                                                    bool at_wall, int bincnt, double size, double vlim2, double2* acc_tmp) {
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
     constexpr int TW = D::TW, NW = D::NW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double2* posb = S.pos[b];
-    double2* posn = S.pos[b ^ 1];
     const int nch = (np + 31) >> 5;
     bool too_fast = false;
 #pragma unroll 1
@@ -553,43 +605,36 @@ static __device__ __forceinline__ void k_move_phase(KSmem<TS, H>& S, int b, int 
         const unsigned w = p < np ? S.pw[p] : 0u;
         const unsigned cnt = w >> kCntShift;
         double ax = 0.0, ay = 0.0;
-        const unsigned slow = __ballot_sync(0xffffffffu, cnt >= 3u);
-        if (slow) {
-            const double2 a = kslow_force<TS, H>(b, slow, p, nvalid, bincnt);
-            if (cnt >= 3u) {
-                ax = a.x;
-                ay = a.y;
-            }
-        }
         if (p < np) {
-            if (cnt == 1u || cnt == 2u) {
+            if (cnt != 0u) {   // 1 or 2 (the canonical-order pass has turned every larger count into "1, its result slot")
                 // (the pair's second particle takes the exact negative: flip the sign bit)
                 auto signed_of = [](double v, unsigned ref) {
                     return __hiloint2double(__double2hiint(v) ^ (int)((ref & kRefNeg) << 18), __double2loint(v));
                 };
-                const double2 c0 = S.wres[w & (kRefNeg - 1u)];
+                const double2 c0 = S.u.w.a.f.wres[w & (kRefNeg - 1u)];
                 ax = __dadd_rn(ax, signed_of(c0.x, w));
                 ay = __dadd_rn(ay, signed_of(c0.y, w));
                 if (cnt == 2u) {
                     const unsigned w1 = w >> kRefBits;
-                    const double2 c1 = S.wres[w1 & (kRefNeg - 1u)];
+                    const double2 c1 = S.u.w.a.f.wres[w1 & (kRefNeg - 1u)];
                     ax = __dadd_rn(ax, signed_of(c1.x, w1));
                     ay = __dadd_rn(ay, signed_of(c1.y, w1));
                 }
             }
             // integrate (reference serial.cpp:46-51); walls (serial.cpp:53-61) only where the loaded region touches one:
             // elsewhere a particle that reaches a wall has left the trusted part of the region anyway
-            const double2 me = posb[p];
-            double2 v = S.vel[p];
+            const int vi = (sorted && p >= n_own) ? (int)S.horig[p - n_own] : p;
+            const double2 me = S.pos[p];
+            double2 v = S.vel[vi];
             v.x = __dadd_rn(v.x, __dmul_rn(ax, kDt));
             v.y = __dadd_rn(v.y, __dmul_rn(ay, kDt));
             double x = __dadd_rn(me.x, __dmul_rn(v.x, kDt)), y = __dadd_rn(me.y, __dmul_rn(v.y, kDt));
             too_fast |= !(__fma_rn(v.x, v.x, __dmul_rn(v.y, v.y)) < vlim2);
-            posn[p] = make_double2(x, y);
-            S.vel[p] = v;
+            S.pos[p] = make_double2(x, y);
+            S.vel[vi] = v;
             if (at_wall) {
-                k_reflect_in_place<TS, H>(b ^ 1, p, size);
-                const double2 q = posn[p];
+                k_reflect_in_place<TS, H>(p, vi, size);
+                const double2 q = S.pos[p];
                 x = q.x;
                 y = q.y;
             }
@@ -612,7 +657,6 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
     using C = KCfg<TS, H>;
     using D = KDims<TS, H>;
     constexpr int T = C::T, CAP = C::CAP, NMAX = C::NMAX, TW = D::TW, RW = D::RW, NW = D::NW;
-    constexpr int kIdRegs = (CAP + T - 1) / T;
 
     extern __shared__ __align__(128) unsigned char k_smem_raw[];
     KSmem<TS, H>& S = *reinterpret_cast<KSmem<TS, H>*>(k_smem_raw);
@@ -625,16 +669,18 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
     const int G = gridDim.x;
 
     if (tid == 0) {
-        k_mbar_init(&S.mbar, 1);
+        k_mbar_init(&S.mbar_p, 1);
+        k_mbar_init(&S.mbar_v, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.flags = 0;
         S.hw_region = S.hw_stripe = S.hw_pairs = 0;
     }
     if (tid < 9) S.segcnt[tid] = 0;
     if (tid < 8) S.ringcnt[tid] = 0;
-    // ---- loader (warp 0) ---------------------------------------------------------------------------------------------------
+    // ---- loader (the last warp) --------------------------------------------------------------------------------------------
     // Slot range `lane` (< kRanges) of the region of launch tile t: length and first global slot.  The headers of a tile are
-    // fetched one tile before its bulk copies are issued, the bulk copies one tile before the data is used.
+    // fetched one tile before its bulk copies are issued; its positions are copied while the previous tile is stored, its
+    // velocities as soon as the previous tile's have been stored.
     // (the loader is the LAST warp: it has the fewest particle chunks; tiles are walked without divisions)
     constexpr int kLoader = NW - 1;
     const int walk_q = (G / P.ntx) * P.row_stride, walk_r = G % P.ntx;
@@ -667,9 +713,9 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
         }
         advance(fw);
     };
-    // Publish the ranges of a tile in slot set q and issue its bulk copies: positions into position buffer pb, velocities into
-    // the landing zone (the cell table's storage, dead between the last search of a tile and the wipe of the next one).
-    auto issue_load = [&](int len, int src, int q, int pb) {
+    // Publish the ranges of a tile in slot set q and bulk-copy its positions into the landing zone (the storage of the cell
+    // table / force lists / candidate pairs, dead between the last sub-step of a tile and the wipe of the next one).
+    auto issue_positions = [&](int len, int src, int q) {
         int inc = len;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) {
@@ -692,25 +738,33 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
             S.ncount[q] = n;
             if (total > NMAX) atomicOr(&S.flags, kErrSmemOverflow);
             S.hw_region = max(S.hw_region, total);
-            k_mbar_arrive_expect_tx(&S.mbar, (unsigned)n * 32u);
+            k_mbar_arrive_expect_tx(&S.mbar_p, (unsigned)n * 16u);
         }
         __syncwarp();
-        if (len > 0) {
-            k_tma_load_1d(&S.pos[pb][dst], P.pos_in + src, (unsigned)len * 16u, &S.mbar);
-            k_tma_load_1d(&S.u.vland[dst], P.vel_in + src, (unsigned)len * 16u, &S.mbar);
+        if (len > 0) k_tma_load_1d(&S.u.pland[dst], P.pos_in + src, (unsigned)len * 16u, &S.mbar_p);
+    };
+    // The velocities of the tile whose ranges are published in slot set q go straight into S.vel (load order).
+    auto issue_velocities = [&](int q) {
+        int len = 0, src = 0, dst = 0;
+        if (lane < kRanges) {
+            len = S.rlen[q][lane];
+            src = S.rsrc[q][lane];
+            dst = S.rdst[q][lane];
         }
+        if (lane == 0) k_mbar_arrive_expect_tx(&S.mbar_v, (unsigned)S.ncount[q] * 16u);
+        __syncwarp();
+        if (len > 0) k_tma_load_1d(&S.vel[dst], P.vel_in + src, (unsigned)len * 16u, &S.mbar_v);
     };
     int next_len = 0, next_src = 0;
-    __syncthreads();   // mbarrier initialised
+    __syncthreads();   // mbarriers initialised
     if (warp == kLoader) {
         fetch_range(next_len, next_src);
-        issue_load(next_len, next_src, 0, 0);
+        issue_positions(next_len, next_src, 0);
         fetch_range(next_len, next_src);
     }
 
-    int b0 = 0;   // position buffer that holds the tile's initial positions
     for (int it = 0; cur.t < P.ntiles; ++it, advance(cur)) {
-        const int q = it & 1, t = cur.t;
+        const int q = it & 1;
         const int lrow = cur.lrow, tc = cur.tc;
         const int rbase = (P.tr_base + lrow) * TS - H - kGuard, cbase = tc * TS - H - kGuard;   // global cell of table row / column 0
         const bool at_wall = rbase + kGuard <= 0 || cbase + kGuard <= 0 || rbase + TW - 1 - kGuard >= P.bincnt - 1 ||
@@ -720,45 +774,53 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
         // interior (only particles whose computed state is already worthless can leave the loaded region)
         auto table_cell = [&](double x, double y, int& lr, int& lc) { k_table_cell<TW>(x, y, rbase, cbase, at_wall, P.bincnt, lr, lc); };
 
-        // ---- arrival: velocities leave the landing zone, the halo is ordered by ring -----------------------------------
-        k_mbar_wait(&S.mbar, (unsigned)q);
+        // the previous tile's velocities have been stored (barrier at the end of the loop body): this tile's may land
+        if (warp == kLoader) issue_velocities(q);
+
+        // ---- arrival: positions leave the landing zone, the halo is ordered by ring ------------------------------------
+        k_mbar_wait(&S.mbar_p, (unsigned)q);
         const int n = S.ncount[q];
-        const int n_own = S.rlen[q][0], own_src = S.rsrc[q][0], n_halo = n - n_own;
-        // ids of the tile's own stripe (range 0, shared slots [0, n_own)): loaded now, parked in shared memory after the
-        // barrier below; the few halo particles that end up inside the tile fetch theirs when they are stored
-        int idreg[kIdRegs];
-#pragma unroll
-        for (int k = 0; k < kIdRegs; ++k) idreg[k] = tid + k * T < n_own ? P.id_in[own_src + tid + k * T] : 0;
-        for (int p = tid; p < n_own; p += T) S.vel[p] = S.u.vland[p];
+        const int n_own = S.rlen[q][0], n_halo = n - n_own;
+        for (int p = tid; p < n_own; p += T) S.pos[p] = S.u.pland[p];
         // A halo particle at ring r (cells between it and the tile, 1..H) can influence the tile's final state only through
         // sub-step H - 1 - r, and nothing reads it after sub-step H - r: sorted by ring, the particles that still matter are a
-        // prefix of the region, and the passes of sub-step s simply stop at n_proc[s].  (Skipped when the halo exceeds one
-        // particle per thread.)  Ring and class counters were zeroed at the end of the previous tile.
-        const bool ringsort = P.ringsort && nsub > 0 && n_halo <= T;
-        double2 hpos = make_double2(0.0, 0.0), hvel = make_double2(0.0, 0.0);
-        int hring = 0, hrank = 0;
+        // prefix of the region, and the passes of sub-step s simply stop at n_proc[s].  (Skipped when the halo exceeds HREG
+        // particles per thread.)  Ring and class counters were zeroed at the end of the previous tile.  Only positions are
+        // moved: the velocities stay in load order and are found through horig.
+        const bool ringsort = P.ringsort && nsub > 0 && n_halo <= D::HMAX;
+        double2 hpos[D::HREG];
+        int hcode[D::HREG];
         if (ringsort) {
-            if (tid < n_halo) {
-                hpos = S.pos[b0][n_own + tid];
-                hvel = S.u.vland[n_own + tid];
-                int lr, lc;
-                table_cell(hpos.x, hpos.y, lr, lc);
-                const int er = lr - (H + kGuard), ec = lc - (H + kGuard);
-                const int dr = er < 0 ? -er : (er >= TS ? er - TS + 1 : 0), dc = ec < 0 ? -ec : (ec >= TS ? ec - TS + 1 : 0);
-                hring = min(max(max(dr, dc), 1), H);
-                hrank = atomicAdd(&S.ringcnt[hring], 1);
+#pragma unroll
+            for (int k = 0; k < D::HREG; ++k) {
+                const int h = tid + k * T;
+                hcode[k] = 0;
+                hpos[k] = make_double2(0.0, 0.0);
+                if (h < n_halo) {
+                    hpos[k] = S.u.pland[n_own + h];
+                    int lr, lc;
+                    table_cell(hpos[k].x, hpos[k].y, lr, lc);
+                    const int er = lr - (H + kGuard), ec = lc - (H + kGuard);
+                    const int dr = er < 0 ? -er : (er >= TS ? er - TS + 1 : 0), dc = ec < 0 ? -ec : (ec >= TS ? ec - TS + 1 : 0);
+                    const int ring = min(max(max(dr, dc), 1), H);
+                    hcode[k] = (ring << 16) | atomicAdd(&S.ringcnt[ring], 1);
+                }
             }
         } else {
-            for (int p = n_own + tid; p < n; p += T) S.vel[p] = S.u.vland[p];
+            for (int p = n_own + tid; p < n; p += T) S.pos[p] = S.u.pland[p];
         }
         __syncthreads();   // the landing zone is free (it becomes the cell table again); ring counts complete
         if (ringsort) {
-            if (tid < n_halo) {
-                int o = n_own + hrank;
-                for (int r = 1; r < hring; ++r) o += S.ringcnt[r];
-                S.pos[b0][o] = hpos;
-                S.vel[o] = hvel;
-                S.horig[o - n_own] = (unsigned short)(n_own + tid);
+#pragma unroll
+            for (int k = 0; k < D::HREG; ++k) {
+                const int h = tid + k * T;
+                if (h < n_halo) {
+                    const int ring = hcode[k] >> 16;
+                    int o = hcode[k] & 0xFFFF;
+                    for (int r = 1; r < ring; ++r) o += S.ringcnt[r];
+                    S.pos[n_own + o] = hpos[k];
+                    S.horig[o] = (unsigned short)(n_own + h);
+                }
             }
             if (tid < C::KMAX) {   // sub-step tid processes rings <= H - 1 - tid
                 int c = n_own;
@@ -768,28 +830,25 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
         } else if (tid < C::KMAX) {
             S.nproc[tid] = n;
         }
-#pragma unroll
-        for (int k = 0; k < kIdRegs; ++k)
-            if (tid + k * T < n_own) S.id[tid + k * T] = idreg[k];
         {   // wipe the cell table and the occupancy map
-            uint4* hq = reinterpret_cast<uint4*>(S.u.t.head);
+            uint4* hq = reinterpret_cast<uint4*>(S.u.w.a.t.head);
             for (int c = tid; c < D::NC8 / 8; c += T) hq[c] = make_uint4(0u, 0u, 0u, 0u);
-            uint4* bq = reinterpret_cast<uint4*>(S.u.t.bitmap);
+            uint4* bq = reinterpret_cast<uint4*>(S.u.w.a.t.bitmap);
             for (int c = tid; c < D::BM / 4; c += T) bq[c] = make_uint4(0u, 0u, 0u, 0u);
-            if (tid == 0) S.npairs = S.ncon = S.work = 0;
+            if (tid == 0) S.npairs = S.ncon = S.work = S.nslow[0] = S.nslowslot[0] = 0;
         }
         __syncthreads();
 
         if (nsub == 0) {
             for (int p = tid; p < n; p += T) {
-                const double2 a = S.pos[b0][p];
+                const double2 a = S.pos[p];
                 int lr, lc;
                 table_cell(a.x, a.y, lr, lc);
                 k_classify<TS, H>(S, p, lr, lc);
             }
         } else {
             for (int p = tid; p < n; p += T) {
-                const double2 a = S.pos[b0][p];
+                const double2 a = S.pos[p];
                 int lr, lc;
                 table_cell(a.x, a.y, lr, lc);
                 k_bin_particle<TS, H>(S, p, lr, lc);
@@ -800,35 +859,42 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
 
         // ---- candidate pairs of the whole launch, then the fused time steps ---------------------------------------------
         if (nsub > 0) {
-            k_search<TS, H>(S, b0, n, S.nproc[0], P.rs2);
+            k_search<TS, H>(S, n, S.nproc[0], P.rs2);
             __syncthreads();
-            if (tid == 0 && S.npairs > D::PCAP) atomicOr(&S.flags, kErrSmemOverflow);
+            // the candidate list (from the front) and the first sub-step's in-range list (from the back) must not meet
+            if (tid == 0 && S.npairs + min(S.ncon, D::NCON) > D::PCAP) atomicOr(&S.flags, kErrSmemOverflow);
         }
+        k_mbar_wait(&S.mbar_v, (unsigned)q);   // the velocities have had the whole arrival / binning / search to land
         for (int s = 0; s < nsub; ++s) {
-            const int b = (b0 + s) & 1, np = S.nproc[s], nvalid = s == 0 ? n : S.nproc[s - 1];
+            const int np = S.nproc[s], nvalid = s == 0 ? n : S.nproc[s - 1];
             if (s > 0) {   // (the first sub-step's in-range pairs come from the search)
-                k_pair_check<TS, H>(S, b, np, nvalid);
+                k_pair_check<TS, H>(S, np, nvalid);
                 __syncthreads();
+                k_pair_eval<TS, H>(S, S.u.w.a.f.inlist, 1, np, P.bincnt, s & 1);
+            } else {
+                k_pair_eval<TS, H>(S, S.u.w.pairs + (D::PCAP - 1), -1, np, P.bincnt, 0);
             }
-            k_pair_eval<TS, H>(S, b, np, P.bincnt);
             __syncthreads();
             if (tid == 0) {
-                if (S.ncon > D::NCON) atomicOr(&S.flags, kErrSmemOverflow);
+                if (S.ncon > D::NLIST) atomicOr(&S.flags, kErrSmemOverflow);
                 S.hw_pairs = max(S.hw_pairs, S.ncon);
                 S.ncon = 0;
+                S.nslow[(s + 1) & 1] = S.nslowslot[(s + 1) & 1] = 0;   // (the counters of this sub-step's parity are still being read)
             }
-            k_move_phase<TS, H, kStoreAcc>(S, b, np, nvalid, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size, P.vlim2,
+            if (S.nslow[s & 1] != 0) {   // same value in every thread: written before the barrier above, reset one sub-step later
+                k_slow_phase<TS, H>(np, nvalid, P.bincnt, s & 1);
+                __syncthreads();
+            }
+            k_move_phase<TS, H, kStoreAcc>(S, np, n_own, ringsort, s + 1 == nsub, rbase, cbase, at_wall, P.bincnt, P.size, P.vlim2,
                                            P.acc_tmp + (size_t)blockIdx.x * NMAX);
-            if (s + 1 == nsub) k_fence_proxy_async();   // my accesses to the search tables and the free position buffer precede the next tile's bulk copies
+            if (s + 1 == nsub) k_fence_proxy_async();   // my accesses to the tables / lists precede the next tile's bulk copies into their storage
             __syncthreads();
         }
 
-
-        // ---- store phase: the loader warp issues the next tile's bulk copies while the other warps store this tile ----------
-        const int bf = (b0 + nsub) & 1;   // buffer with the final positions; the other one receives the next tile
+        // ---- store phase: the loader warp issues the next tile's position copies while the other warps store this tile -------
         if (warp == kLoader) {
             if (cur.t + G < P.ntiles) {
-                issue_load(next_len, next_src, q ^ 1, bf ^ 1);
+                issue_positions(next_len, next_src, q ^ 1);
                 fetch_range(next_len, next_src);
             }
         } else {
@@ -844,7 +910,7 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                 if (lane < 10) S.segoff[lane] = inc - v;   // exclusive prefix; [9] = population
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TS_) : "memory");
-            const int lrow_ = cur.lrow, tc_ = cur.tc, lt = lrow_ * P.ntx + tc_;
+            const int lt = lrow * P.ntx + tc;
             const size_t gbase = (size_t)lt * CAP;
             double2* ppos = nullptr;
             double2* pvel = nullptr;
@@ -853,12 +919,12 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
             if (kPeer) {
                 // first owned row -> lower neighbour (needs my top band TL T TR); last owned row -> upper neighbour (BR B BL).
                 // A one-row slab would have to serve both: such slabs use the NCCL flavour (kstep host code).
-                const int side = lrow_ == 1 ? 0 : (lrow_ == P.last_lrow ? 1 : -1);
+                const int side = lrow == 1 ? 0 : (lrow == P.last_lrow ? 1 : -1);
                 if (side >= 0 && P.peer_pos[side]) {
-                    ppos = P.peer_pos[side] + (size_t)tc_ * CAP;
-                    pvel = P.peer_vel[side] + (size_t)tc_ * CAP;
-                    pid = P.peer_id[side] + (size_t)tc_ * CAP;
-                    phdr = P.peer_hdr[side] + (size_t)tc_ * kHdrInts;
+                    ppos = P.peer_pos[side] + (size_t)tc * CAP;
+                    pvel = P.peer_vel[side] + (size_t)tc * CAP;
+                    pid = P.peer_id[side] + (size_t)tc * CAP;
+                    phdr = P.peer_hdr[side] + (size_t)tc * kHdrInts;
                     peer_classes = side == 0 ? 0x007u : 0x070u;
                 }
             }
@@ -871,10 +937,8 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                     S.hw_stripe = max(S.hw_stripe, S.segoff[9]);
                 }
             }
-            const double2* posf = S.pos[bf];
-            const int nfin = nsub > 0 ? S.nproc[nsub - 1] : S.ncount[q];   // particles beyond were never candidates for the tile
-            const int n_own_ = S.rlen[q][0];
-            const bool sorted = P.ringsort && nsub > 0 && S.ncount[q] - n_own_ <= T;
+            const int nfin = nsub > 0 ? S.nproc[nsub - 1] : n;   // particles beyond were never candidates for the tile
+            const int own_src = S.rsrc[q][0];
 #pragma unroll 1
             for (int p = tid; p < nfin; p += TS_) {
                 const unsigned oc = S.pw[p];
@@ -882,18 +946,18 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                 const unsigned cls = oc >> 12;
                 const int d = S.segoff[cls] + (int)(oc & 0xFFFu);
                 if (d >= CAP) continue;
-                const double2 pq = posf[p], v = S.vel[p];
-                int id;
-                if (p < n_own_) {
-                    id = S.id[p];
+                int id, vi = p;
+                if (p < n_own) {
+                    id = P.id_in[own_src + p];
                 } else {   // a halo particle that moved into the tile: find its source slot
-                    const int po = sorted ? (int)S.horig[p - n_own_] : p;   // its slot before the ring sort
+                    if (ringsort) vi = (int)S.horig[p - n_own];   // its slot in load order
                     id = 0;
                     for (int g = 1; g < kRanges; ++g) {
-                        const int o = po - S.rdst[q][g];
+                        const int o = vi - S.rdst[q][g];
                         if ((unsigned)o < (unsigned)S.rlen[q][g]) id = P.id_in[S.rsrc[q][g] + o];
                     }
                 }
+                const double2 pq = S.pos[p], v = S.vel[vi];
                 P.pos_out[gbase + d] = pq;
                 P.vel_out[gbase + d] = v;
                 P.id_out[gbase + d] = id;
@@ -904,12 +968,12 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                     pid[d] = id;
                 }
             }
+            k_fence_proxy_async();   // my reads of the velocities precede the next tile's bulk copy into S.vel
             asm volatile("bar.sync 1, %0;" ::"n"(TS_) : "memory");   // class counters have been read by everybody
             if (tid < 9) S.segcnt[tid] = 0;
             if (tid < 8) S.ringcnt[tid] = 0;
         }
-        b0 = bf ^ 1;
-        __syncthreads();   // the tile is completely stored: velocities, codes and the final position buffer may be overwritten
+        __syncthreads();   // the tile is completely stored: positions, velocities and codes may be overwritten
     }
     // ---- report ------------------------------------------------------------------------------------------------------
     __syncthreads();
@@ -1309,6 +1373,9 @@ int kstep_create(psim_sim* sim, const psim_config* cfg, const particle_t* parts,
     PSIM_TRY(e->mem.alloc(&e->acc_tmp, (size_t)2 * e->grid_cap * e->nmax));   // (x2: a slab's boundary and interior launches run concurrently)
     PSIM_TRY(e->mem.alloc(&e->tcount, tiles));
     PSIM_CUDA(cudaMemsetAsync(e->tcount, 0, sizeof(int) * tiles, s));
+    if (trace)
+        std::fprintf(stderr, "[psim trace] kstep_create rank %d: %d-cell tiles, halo %d, %d threads x %d CTAs per SM, %zu bytes of shared memory per CTA\n",
+                     sim->rank, e->ts, e->h, e->threads, e->ctas_per_sm, e->smem);
     lap("configure + allocate");
     // Slabs with a host array: by default the upload is cooperative and happens in psim_comm_connect (kstep_distributed_fill)
     static const bool coop = !(std::getenv("PSIM_COOP_UPLOAD") && std::getenv("PSIM_COOP_UPLOAD")[0] == '0');

@@ -4,7 +4,7 @@
 C=parallel-particle-simulation_b200/csrc
 mkdir -p gpurun_out
 run() { # tag lib tile
-  PSIM_LIB=$PWD/$C/$2/libpsim.so python bench.py --tile $3 --steps 600 --warmup 20 --no-cpu-baseline --no-e2e > gpurun_out/sweep_$1.json 2> gpurun_out/sweep_$1.err
+  PSIM_LIB=$PWD/$C/$2/libpsim.so python bench.py --tile $3 --steps ${STEPS:-600} --warmup 20 --no-cpu-baseline --no-e2e $EXTRA_ARGS > gpurun_out/sweep_$1.json 2> gpurun_out/sweep_$1.err
   python - <<PY
 import json
 try:
