@@ -899,6 +899,13 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
             }
         } else {
             constexpr int TS_ = T - 32;   // storing threads (named barrier 1)
+            // the ids of the tile's own stripe (shared slots [0, n_own)) are requested now, all at once: their latency hides
+            // behind the header work and the barrier below instead of being paid once per loop iteration
+            constexpr int kIdRegs = (CAP + TS_ - 1) / TS_;
+            const int own_src = S.rsrc[q][0];
+            int idreg[kIdRegs];
+#pragma unroll
+            for (int k = 0; k < kIdRegs; ++k) idreg[k] = tid + k * TS_ < n_own ? P.id_in[own_src + tid + k * TS_] : 0;
             // class offsets -> header, particles -> the other parity's stripe
             if (warp == 0) {
                 int v = lane < 9 ? S.segcnt[lane] : 0, inc = v;
@@ -938,18 +945,14 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                 }
             }
             const int nfin = nsub > 0 ? S.nproc[nsub - 1] : n;   // particles beyond were never candidates for the tile
-            const int own_src = S.rsrc[q][0];
-#pragma unroll 1
-            for (int p = tid; p < nfin; p += TS_) {
+            auto store_one = [&](int p, int own_id) {
                 const unsigned oc = S.pw[p];
-                if (oc == kNoOwner) continue;
+                if (oc == kNoOwner) return;
                 const unsigned cls = oc >> 12;
                 const int d = S.segoff[cls] + (int)(oc & 0xFFFu);
-                if (d >= CAP) continue;
-                int id, vi = p;
-                if (p < n_own) {
-                    id = P.id_in[own_src + p];
-                } else {   // a halo particle that moved into the tile: find its source slot
+                if (d >= CAP) return;
+                int id = own_id, vi = p;
+                if (p >= n_own) {   // a halo particle that moved into the tile: find its source slot
                     if (ringsort) vi = (int)S.horig[p - n_own];   // its slot in load order
                     id = 0;
                     for (int g = 1; g < kRanges; ++g) {
@@ -967,7 +970,12 @@ __global__ void __launch_bounds__(KCfg<TS, H>::T, KCfg<TS, H>::CTAS) kstep_kerne
                     pvel[d] = v;
                     pid[d] = id;
                 }
-            }
+            };
+#pragma unroll
+            for (int k = 0; k < kIdRegs; ++k)
+                if (tid + k * TS_ < nfin) store_one(tid + k * TS_, idreg[k]);
+#pragma unroll 1
+            for (int p = tid + kIdRegs * TS_; p < nfin; p += TS_) store_one(p, 0);   // (beyond the stripe capacity: halo particles only)
             k_fence_proxy_async();   // my reads of the velocities precede the next tile's bulk copy into S.vel
             asm volatile("bar.sync 1, %0;" ::"n"(TS_) : "memory");   // class counters have been read by everybody
             if (tid < 9) S.segcnt[tid] = 0;
