@@ -33,14 +33,20 @@
 // ranges (own stripe, four edge bands -- the E neighbour's left band wraps around the ring and takes two -- and four
 // corners), each one TMA bulk copy (cp.async.bulk -> UBLKCP) for pos and one for vel, completion on an mbarrier.
 //
-// The kernel (kstep_kernel<TS, H, acc, peer>): persistent CTAs, one tile at a time, T threads:
-//   load     (one tile ahead, by the last warp) headers of the next tile are fetched while the current one computes; its 10
-//            ranges are bulk-copied the moment the current tile's last search is over -- positions into the position buffer
-//            that tile no longer needs, velocities into a landing zone that aliases the (then dead) cell table -- so the
-//            copies fly during the store phase, from which the loader warp is excused (named barrier of the other warps)
-//   arrive   velocities leave the landing zone, the halo is ring-sorted, own ids are parked, the cell table is wiped
-//   bin      every loaded particle into a (TS+2H+4)^2 cell table (tile + halo + two empty guard rings) in shared memory: per cell the head of a linked list
-//            (reference part3/gpu.cu:92-112 does this in global memory with 16 fixed slots) + one occupancy bit
+// The kernel (kstep_kernel<TS, H, acc, peer>): persistent CTAs, one tile at a time, T threads.  Shared memory is what decides
+// how many CTAs share an SM, and the other CTAs are what fills a tile's barrier waits and serial stretches, so the layout is
+// lean (72 KB for a 64-cell tile: three CTAs of 256 threads per SM): ONE position array updated in place, velocities in load
+// order, and one work area that is the cell table during the search, the force lists during the sub-steps and the landing zone
+// of the next tile's positions during the store phase.
+//   load     (by the last warp) the headers of the next tile are fetched while the current one computes.  Its POSITIONS are
+//            bulk-copied into the work area the moment the current tile's last sub-step is over, so they fly during the store
+//            phase (the loader warp is excused from it: named barrier of the other warps); its VELOCITIES go straight into the
+//            velocity array as soon as the current tile has been stored and are first needed after the search.
+//   arrive   positions leave the landing zone -- the halo ring-sorted (velocities stay in load order and are found through
+//            horig) --, the cell table is wiped
+//   bin      every loaded particle into a (TS+2H+4)^2 cell table (tile + halo + two empty guard rings) in shared memory: per cell
+//            the head of a linked list (reference part3/gpu.cu:92-112 does this in global memory with 16 fixed slots) + one
+//            occupancy bit
 //   search   ONCE per tile: every particle walks the earlier half of its 5x5 cell neighbourhood (so each unordered pair is met
 //            once) and lists the pairs within rs = cutoff + the distance two particles can close in the remaining sub-steps
 //            (the speed bound is enforced below): the tile's candidate-pair list, ~1.25 pairs per particle.  Pairs that are
@@ -51,9 +57,9 @@
 //                    reference serial.cpp:29-33 run once per PAIR (the second particle takes the exact negative); the
 //                    reference's 3x3 cell structure (serial.cpp:102-117) is re-imposed exactly here.  Each particle's
 //                    force word counts its in-range neighbours and remembers its first two pairs
-//            move    sum (<= 2 terms are order independent; >= 3 take the canonical-order exact path), move + reflect
-//                    (serial.cpp:46-61), speed check; after the last sub-step: final cell -> class
-//            positions are double buffered by sub-step parity
+//            (slow)  only if some particle has >= 3 in-range neighbours: their sums in the canonical exact order
+//            move    sum (<= 2 terms are order independent), move + reflect (serial.cpp:46-61) in place, speed check; after
+//                    the last sub-step: final cell -> class
 //   store    particles whose final cell lies in the tile are ranked inside their class (shared atomics), the class
 //            offsets become the tile's new header, and pos / vel / id (/ acc) are stored to the other parity.  Tiles
 //            of a slab's first / last row also store their facing band straight into the neighbour GPU's ghost row.
