@@ -2,7 +2,8 @@
 """bench.py -- BASELINE.json's metric on BASELINE.json's configuration.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles P]
-                    [--engine auto|tiled|cellsort] [--tile 16|32|64] [--scaling strong|weak]
+                    [--engine auto|kstep|tiled|cellsort] [--tile 16|32|48|64] [--scaling strong|weak]
+                    [--e2e-passes 5] [--no-e2e] [--no-cpu-baseline]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 metric  particle-steps/sec = particles x steps / seconds                     
@@ -13,8 +14,9 @@ N > 1   the same 20 M particles cut into N slabs of tile rows (strong scaling); 
         20 M per GPU
 value   steps only, state resident in HBM, CUDA events on the launching stream, max over ranks
 e2e     psim_create from a PINNED HOST array (H2D inside) + K steps + psim_read_particles back
-        into the host array (D2H inside), wall clock -- the reference driver's own timed region
-        (part1/main.cpp:120-144) plus the final read-back
+        into a second pinned host array (D2H inside), wall clock -- the reference driver's own timed
+        region (part1/main.cpp:120-144) plus the final read-back; one untimed warm-up pass, then the
+        MEDIAN of --e2e-passes passes run back to back (every sample is in the JSON line)
 roofline   dominant kernel = the whole step (one fused kernel for the tiled engine); algorithmic
         bytes 80 B per particle-step (read x y vx vy, write x y vx vy ax ay) against the
         measured HBM copy bandwidth in MEASURED_PEAKS.json

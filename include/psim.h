@@ -72,7 +72,7 @@ typedef struct psim_config {
     int   engine;        /* PSIM_ENGINE_*                                                        */
     int   device;        /* CUDA device ordinal; -1 = the calling thread's current device        */
     void* stream;        /* cudaStream_t to run on; NULL = a private non-blocking stream         */
-    int   tile_cells;    /* tiled / kstep engines: cutoff cells per tile side (16, 32 or 64); 0 = auto */
+    int   tile_cells;    /* tiled / kstep engines: cutoff cells per tile side (16, 32 or 64; kstep also 48); 0 = auto */
     int   steps_per_launch; /* kstep engine: time steps fused per kernel launch, 1 .. 3; 0 = default (3, or PSIM_KSTEPS) */
     /* 1-D slab decomposition.  nranks == 1: the whole box.               */
     int   rank;          /* this slab's index along x (cell rows)                                */
