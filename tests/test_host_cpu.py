@@ -75,7 +75,7 @@ def test_slab_rows_rejects_bad_arguments(pkg):
     with pytest.raises(pkg.PsimError):
         pkg.slab_rows(100, 3, 2)
     with pytest.raises(pkg.PsimError):
-        pkg.slab_rows(100, 0, 2, 48)
+        pkg.slab_rows(100, 0, 2, 40)     # not a tile size of this build (16, 32, 48, 64)
     with pytest.raises(pkg.PsimError):
         pkg.slab_rows(71, 0, 9, 16)      # 5 tile rows cannot feed 9 slabs
     assert pkg.slab_rows(71, 0, 1, 16) == (0, 71)
