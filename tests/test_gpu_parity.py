@@ -19,7 +19,7 @@ from psim_testlib import GOLDEN_DIR, REF_DIR, RefKernel, box_size, have_ref, loa
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["cellsort", "tiled16", "tiled32", "tiled64", "kstep16", "kstep32", "kstep64"]
+ENGINES = ["cellsort", "tiled16", "tiled32", "tiled64", "kstep16", "kstep32", "kstep48", "kstep64"]
 
 
 def make_sim(pkg, parts, size, engine):
@@ -252,7 +252,7 @@ def test_pair_list_overflow_takes_the_exact_path(pkg, oracle, engine):
     sim.close()
 
 
-@pytest.mark.parametrize("engine", ["kstep16", "kstep32", "kstep64"])
+@pytest.mark.parametrize("engine", ["kstep16", "kstep32", "kstep48", "kstep64"])
 def test_kstep_canonical_order_path_in_fused_launches(pkg, oracle, engine):
     """Particles with three or more in-range neighbours INSIDE a fused 3-step launch: the kstep kernel counts a particle's
     in-range pairs in its force word and, from three on, collects the partners from the tile's candidate-pair list and sums them
