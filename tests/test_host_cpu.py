@@ -79,6 +79,8 @@ def test_slab_rows_rejects_bad_arguments(pkg):
     with pytest.raises(pkg.PsimError):
         pkg.slab_rows(71, 0, 9, 16)      # 5 tile rows cannot feed 9 slabs
     assert pkg.slab_rows(71, 0, 1, 16) == (0, 71)
+    assert pkg.slab_rows(100, 0, 2, 48) == (0, 96)   # 3 tile rows of 48 cells: two for rank 0, the (partial) third for rank 1
+    assert pkg.slab_rows(100, 1, 2, 48) == (96, 100)
 
 
 def test_reference_arm_only_rank0_works(tmp_path):
