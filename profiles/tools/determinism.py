@@ -21,10 +21,13 @@ hashes = {}
 for name, env, tile, engine in [("kstep64 K3 H4", {}, 64, "kstep"), ("kstep64 again", {}, 64, "kstep"), ("kstep64 1cta", {"PSIM_CTAS_PER_SM": "1"}, 64, "kstep"),
                                 ("kstep64 K2", {"PSIM_KSTEPS": "2"}, 64, "kstep"), ("kstep64 K1", {"PSIM_KSTEPS": "1"}, 64, "kstep"),
                                 ("kstep64 H3 K2", {"PSIM_HALO": "3"}, 64, "kstep"), ("kstep64 noring", {"PSIM_RINGSORT": "0"}, 64, "kstep"),
+                                ("kstep64 2cta", {"PSIM_CTAS_PER_SM": "2"}, 64, "kstep"), ("kstep48", {}, 48, "kstep"),
                                 ("kstep32", {}, 32, "kstep"), ("kstep16", {}, 16, "kstep"),
                                 ("t32 4cta", {}, 32, "tiled"), ("t32 4cta again", {}, 32, "tiled"), ("t32 1cta", {"PSIM_CTAS_PER_SM": "1"}, 32, "tiled"),
                                 ("t32 3cta", {"PSIM_CTAS_PER_SM": "3"}, 32, "tiled"), ("t16", {}, 16, "tiled"), ("t64", {}, 64, "tiled"),
                                 ("cellsort", {}, 0, "cellsort")]:
+    if len(sys.argv) > 3 and sys.argv[3] == "kstep-only" and engine == "tiled":   # (the tiled engine did not change this round-half)
+        continue
     r = subprocess.run([sys.executable, __file__, "child", str(n), str(steps), str(tile), engine], capture_output=True, text=True,
                        env=dict(os.environ, **env))
     line = [l for l in r.stdout.splitlines() if l.startswith("HASH")]
